@@ -1,0 +1,315 @@
+// api.cu -- extern "C" entry points taking HOST buffers (copies + kernels + copy back), and the
+// device-pointer variant used for HBM-resident timing.  See include/statdepth_b200.h.
+#include <vector>
+
+#include "common.cuh"
+
+namespace sd {
+
+// dispatch one subset size j on device-resident data
+int band_depth_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq, int j,
+                      int relax, i64 *d_out) {
+    if (j != 2 && j != 3) {
+        set_error("band depth: subset size j=%d not supported on the device (2 or 3)", j);
+        return SD_ERR_UNSUPPORTED;
+    }
+    if (!relax) {
+        if (j == 2 && ctx->bd_impl == SD_BD_GEMM) return bd_strict_gemm_device(ctx, dX, T, n, ld, d_q, nq, d_out);
+        return bd_strict_device(ctx, dX, T, n, ld, d_q, nq, j, d_out);
+    }
+    // overflow guard: T * C(n-1, j) must fit in int64
+    {
+        const long double full = (j == 2) ? (long double)(n - 1) * (n - 2) / 2.0L
+                                          : (long double)(n - 1) * (n - 2) * (n - 3) / 6.0L;
+        if (full * (long double)(T > 0 ? T : 1) >= 9.0e18L) {
+            set_error("band depth: T*C(n-1,%d) overflows int64 for T=%lld n=%lld", j, (long long)T, (long long)n);
+            return SD_ERR_OVERFLOW;
+        }
+    }
+    SD_TRY(ctx->buf[BUF_ACC].reserve((size_t)n * 2 * sizeof(i64)));
+    i64 *acc2 = ctx->buf[BUF_ACC].as<i64>();
+    i64 *acc3 = acc2 + n;
+    SD_TRY(mbd_all_device(ctx, dX, T, n, ld, j == 3, acc2, acc3, nullptr, nullptr));
+    return gather_i64_device(ctx, j == 2 ? acc2 : acc3, d_q, nq, d_out);
+}
+
+static int check_common(sd_ctx *ctx, const void *in, const void *out, const char *who) {
+    if (!ctx) {
+        set_error("%s: NULL context", who);
+        return SD_ERR_INVALID;
+    }
+    if (!in || !out) {
+        set_error("%s: NULL buffer", who);
+        return SD_ERR_INVALID;
+    }
+    return SD_OK;
+}
+
+// upload helper: host matrix [rows, cols] with leading dimension ld -> dense device [rows, cols]
+static int upload_matrix(sd_ctx *ctx, int slot, const double *h, i64 rows, i64 cols, i64 ld, double **d) {
+    SD_TRY(ctx->buf[slot].reserve((size_t)(rows * cols > 0 ? rows * cols : 1) * sizeof(double)));
+    *d = ctx->buf[slot].as<double>();
+    if (rows == 0 || cols == 0) return SD_OK;
+    if (ld == cols || rows == 1) {
+        SD_CUDA(cudaMemcpyAsync(*d, h, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        SD_CUDA(cudaMemcpy2DAsync(*d, (size_t)cols * sizeof(double), h, (size_t)ld * sizeof(double),
+                                  (size_t)cols * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    }
+    return SD_OK;
+}
+
+static int upload_queries(sd_ctx *ctx, const int64_t *h_q, i64 nq, i64 n, const i64 **d_q, const char *who) {
+    *d_q = nullptr;
+    if (!h_q) {
+        if (nq != n) {
+            set_error("%s: query_idx == NULL requires nq == n", who);
+            return SD_ERR_INVALID;
+        }
+        return SD_OK;
+    }
+    for (i64 i = 0; i < nq; ++i)
+        if (h_q[i] < 0 || h_q[i] >= n) {
+            set_error("%s: query_idx[%lld]=%lld out of range [0,%lld)", who, (long long)i, (long long)h_q[i],
+                      (long long)n);
+            return SD_ERR_INVALID;
+        }
+    SD_TRY(ctx->buf[BUF_MISC].reserve((size_t)(nq > 0 ? nq : 1) * sizeof(i64)));
+    i64 *dq = ctx->buf[BUF_MISC].as<i64>();
+    if (nq > 0)
+        SD_CUDA(cudaMemcpyAsync(dq, h_q, (size_t)nq * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
+    *d_q = dq;
+    return SD_OK;
+}
+
+}  // namespace sd
+
+using namespace sd;
+
+extern "C" {
+
+int sd_band_depth_f64(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_t ld, int layout,
+                      const int64_t *query_idx, int64_t nq, int j, int relax, int64_t *count_out) {
+    SD_TRY(check_common(ctx, X, count_out, "sd_band_depth_f64"));
+    SD_REQUIRE(T >= 1 && n >= 1 && nq >= 0, "sd_band_depth_f64: bad sizes T=%lld n=%lld nq=%lld", (long long)T,
+               (long long)n, (long long)nq);
+    SD_REQUIRE(layout == SD_LAYOUT_TN || layout == SD_LAYOUT_NT, "sd_band_depth_f64: bad layout %d", layout);
+    SD_REQUIRE(ld >= (layout == SD_LAYOUT_TN ? n : T), "sd_band_depth_f64: ld=%lld too small", (long long)ld);
+    SD_TRY(begin_call(ctx));
+    double *dX = nullptr;
+    if (layout == SD_LAYOUT_TN) {
+        SD_TRY(upload_matrix(ctx, BUF_IN, X, T, n, ld, &dX));
+    } else {  // [n, T] curve-major: upload, then transpose on the device
+        double *dN = nullptr;
+        SD_TRY(upload_matrix(ctx, BUF_IN2, X, n, T, ld, &dN));
+        SD_TRY(ctx->buf[BUF_IN].reserve((size_t)T * n * sizeof(double)));
+        dX = ctx->buf[BUF_IN].as<double>();
+    }
+    const i64 *d_q = nullptr;
+    SD_TRY(upload_queries(ctx, query_idx, nq, n, &d_q, "sd_band_depth_f64"));
+    SD_TRY(ctx->buf[BUF_OUT].reserve((size_t)(nq > 0 ? nq : 1) * sizeof(i64)));
+    i64 *d_out = ctx->buf[BUF_OUT].as<i64>();
+    SD_TRY(mark(ctx, 1));
+    if (layout == SD_LAYOUT_NT) SD_TRY(transpose_device(ctx, ctx->buf[BUF_IN2].as<double>(), n, T, T, dX));
+    SD_TRY(band_depth_device(ctx, dX, T, n, n, d_q, nq, j, relax, d_out));
+    SD_TRY(mark(ctx, 2));
+    if (nq > 0)
+        SD_CUDA(cudaMemcpyAsync(count_out, d_out, (size_t)nq * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx, true);
+}
+
+int sd_band_depth_f64_dev(sd_ctx *ctx, const double *dX, int64_t T, int64_t n, int64_t ld,
+                          const int64_t *d_query_idx, int64_t nq, int j, int relax, int64_t *d_count_out) {
+    SD_TRY(check_common(ctx, dX, d_count_out, "sd_band_depth_f64_dev"));
+    SD_REQUIRE(T >= 1 && n >= 1 && nq >= 0 && ld >= n, "sd_band_depth_f64_dev: bad sizes");
+    SD_REQUIRE(d_query_idx || nq == n, "sd_band_depth_f64_dev: query_idx == NULL requires nq == n");
+    SD_TRY(begin_call(ctx));
+    SD_TRY(mark(ctx, 1));
+    SD_TRY(band_depth_device(ctx, dX, T, n, ld, (const i64 *)d_query_idx, nq, j, relax, (i64 *)d_count_out));
+    SD_TRY(mark(ctx, 2));
+    return end_call(ctx, false);
+}
+
+int sd_band_ranks_f64(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_t ld, int layout,
+                      int32_t *below_out, int32_t *above_out) {
+    SD_TRY(check_common(ctx, X, below_out, "sd_band_ranks_f64"));
+    SD_REQUIRE(above_out != nullptr, "sd_band_ranks_f64: above_out is NULL");
+    SD_REQUIRE(T >= 1 && n >= 1, "sd_band_ranks_f64: bad sizes");
+    SD_REQUIRE(layout == SD_LAYOUT_TN || layout == SD_LAYOUT_NT, "sd_band_ranks_f64: bad layout %d", layout);
+    SD_REQUIRE(ld >= (layout == SD_LAYOUT_TN ? n : T), "sd_band_ranks_f64: ld too small");
+    SD_TRY(begin_call(ctx));
+    double *dX = nullptr;
+    if (layout == SD_LAYOUT_TN) {
+        SD_TRY(upload_matrix(ctx, BUF_IN, X, T, n, ld, &dX));
+    } else {
+        double *dN = nullptr;
+        SD_TRY(upload_matrix(ctx, BUF_IN2, X, n, T, ld, &dN));
+        SD_TRY(ctx->buf[BUF_IN].reserve((size_t)T * n * sizeof(double)));
+        dX = ctx->buf[BUF_IN].as<double>();
+    }
+    SD_TRY(ctx->buf[BUF_ACC].reserve((size_t)n * 2 * sizeof(i64)));
+    SD_TRY(ctx->buf[BUF_OUT].reserve((size_t)T * n * 2 * sizeof(int)));
+    int *d_b = ctx->buf[BUF_OUT].as<int>();
+    int *d_a = d_b + (size_t)T * n;
+    SD_TRY(mark(ctx, 1));
+    if (layout == SD_LAYOUT_NT) SD_TRY(transpose_device(ctx, ctx->buf[BUF_IN2].as<double>(), n, T, T, dX));
+    i64 *acc2 = ctx->buf[BUF_ACC].as<i64>();
+    SD_TRY(mbd_all_device(ctx, dX, T, n, n, false, acc2, acc2 + n, d_b, d_a));
+    SD_TRY(mark(ctx, 2));
+    SD_CUDA(cudaMemcpyAsync(below_out, d_b, (size_t)T * n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(cudaMemcpyAsync(above_out, d_a, (size_t)T * n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx, true);
+}
+
+int sd_simplex_depth_f64(sd_ctx *ctx, const double *F, int64_t N, int64_t T, int d, const int64_t *query_idx,
+                         int64_t nq, int relax, double tol, int64_t *count_out) {
+    SD_TRY(check_common(ctx, F, count_out, "sd_simplex_depth_f64"));
+    SD_REQUIRE(N >= 1 && T >= 1 && nq >= 0, "sd_simplex_depth_f64: bad sizes");
+    SD_REQUIRE(d >= 1 && d <= 3, "sd_simplex_depth_f64: d=%d not supported (1..3)", d);
+    SD_REQUIRE(tol >= 0.0, "sd_simplex_depth_f64: tol must be >= 0");
+    SD_TRY(begin_call(ctx));
+    double *dF = nullptr;
+    SD_TRY(upload_matrix(ctx, BUF_IN, F, 1, N * T * d, N * T * d, &dF));
+    const i64 *d_q = nullptr;
+    SD_TRY(upload_queries(ctx, query_idx, nq, N, &d_q, "sd_simplex_depth_f64"));
+    SD_TRY(ctx->buf[BUF_OUT].reserve((size_t)(nq > 0 ? nq : 1) * sizeof(i64)));
+    i64 *d_out = ctx->buf[BUF_OUT].as<i64>();
+    SD_TRY(mark(ctx, 1));
+    SD_TRY(simplex_depth_device(ctx, dF, N, T, d, d_q, nq, relax, tol, d_out));
+    SD_TRY(mark(ctx, 2));
+    if (nq > 0)
+        SD_CUDA(cudaMemcpyAsync(count_out, d_out, (size_t)nq * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx, true);
+}
+
+int sd_pointcloud_simplicial_f64(sd_ctx *ctx, const double *P, int64_t n, int d, const int64_t *query_idx,
+                                 int64_t nq, double tol, int64_t *count_out) {
+    SD_TRY(check_common(ctx, P, count_out, "sd_pointcloud_simplicial_f64"));
+    SD_REQUIRE(n >= 1 && nq >= 0, "sd_pointcloud_simplicial_f64: bad sizes");
+    SD_REQUIRE(d >= 1 && d <= 3, "sd_pointcloud_simplicial_f64: d=%d not supported (1..3)", d);
+    SD_REQUIRE(tol >= 0.0, "sd_pointcloud_simplicial_f64: tol must be >= 0");
+    SD_TRY(begin_call(ctx));
+    double *dP = nullptr;
+    SD_TRY(upload_matrix(ctx, BUF_IN, P, 1, n * d, n * d, &dP));
+    const i64 *d_q = nullptr;
+    SD_TRY(upload_queries(ctx, query_idx, nq, n, &d_q, "sd_pointcloud_simplicial_f64"));
+    SD_TRY(ctx->buf[BUF_OUT].reserve((size_t)(nq > 0 ? nq : 1) * sizeof(i64)));
+    i64 *d_out = ctx->buf[BUF_OUT].as<i64>();
+    SD_TRY(mark(ctx, 1));
+    SD_TRY(simplicial_device(ctx, dP, n, d, d_q, nq, tol, d_out));
+    SD_TRY(mark(ctx, 2));
+    if (nq > 0)
+        SD_CUDA(cudaMemcpyAsync(count_out, d_out, (size_t)nq * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx, true);
+}
+
+int sd_pointcloud_l1_f64(sd_ctx *ctx, const double *P, int64_t n, int d, const int64_t *query_idx, int64_t nq,
+                         double *depth_out) {
+    SD_TRY(check_common(ctx, P, depth_out, "sd_pointcloud_l1_f64"));
+    SD_REQUIRE(n >= 1 && nq >= 0, "sd_pointcloud_l1_f64: bad sizes");
+    SD_REQUIRE(d >= 1 && d <= 16, "sd_pointcloud_l1_f64: d=%d not supported (1..16)", d);
+    SD_TRY(begin_call(ctx));
+    double *dP = nullptr;
+    SD_TRY(upload_matrix(ctx, BUF_IN, P, 1, n * d, n * d, &dP));
+    const i64 *d_q = nullptr;
+    SD_TRY(upload_queries(ctx, query_idx, nq, n, &d_q, "sd_pointcloud_l1_f64"));
+    SD_TRY(ctx->buf[BUF_OUT].reserve((size_t)(nq > 0 ? nq : 1) * sizeof(double)));
+    double *d_out = ctx->buf[BUF_OUT].as<double>();
+    SD_TRY(mark(ctx, 1));
+    SD_TRY(l1_device(ctx, dP, n, d, d_q, nq, d_out));
+    SD_TRY(mark(ctx, 2));
+    if (nq > 0)
+        SD_CUDA(cudaMemcpyAsync(depth_out, d_out, (size_t)nq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx, true);
+}
+
+int sd_pointcloud_oja_f64(sd_ctx *ctx, const double *P, int64_t n, int d, const int64_t *query_idx, int64_t nq,
+                          const int64_t *pool, int64_t npool, double hull_volume, double *out) {
+    SD_TRY(check_common(ctx, P, out, "sd_pointcloud_oja_f64"));
+    SD_REQUIRE(n >= 1 && nq >= 0 && npool >= 0, "sd_pointcloud_oja_f64: bad sizes");
+    SD_REQUIRE(d == 2 || d == 3, "sd_pointcloud_oja_f64: d=%d not supported (2 or 3)", d);
+    SD_REQUIRE(pool || npool == n, "sd_pointcloud_oja_f64: pool == NULL requires npool == n");
+    SD_TRY(begin_call(ctx));
+    double *dP = nullptr;
+    SD_TRY(upload_matrix(ctx, BUF_IN, P, 1, n * d, n * d, &dP));
+    const i64 *d_q = nullptr;
+    SD_TRY(upload_queries(ctx, query_idx, nq, n, &d_q, "sd_pointcloud_oja_f64"));
+    const i64 *d_pool = nullptr;
+    if (pool) {
+        for (i64 i = 0; i < npool; ++i)
+            SD_REQUIRE(pool[i] >= 0 && pool[i] < n, "sd_pointcloud_oja_f64: pool[%lld] out of range", (long long)i);
+        SD_TRY(ctx->buf[BUF_AUX].reserve((size_t)(npool > 0 ? npool : 1) * sizeof(i64)));
+        if (npool > 0)
+            SD_CUDA(cudaMemcpyAsync(ctx->buf[BUF_AUX].p, pool, (size_t)npool * sizeof(i64), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+        d_pool = ctx->buf[BUF_AUX].as<i64>();
+    }
+    SD_TRY(ctx->buf[BUF_OUT].reserve((size_t)(nq > 0 ? nq : 1) * sizeof(double)));
+    double *d_out = ctx->buf[BUF_OUT].as<double>();
+    SD_TRY(mark(ctx, 1));
+    SD_TRY(oja_device(ctx, dP, n, d, d_q, nq, d_pool, npool, hull_volume, d_out));
+    SD_TRY(mark(ctx, 2));
+    if (nq > 0)
+        SD_CUDA(cudaMemcpyAsync(out, d_out, (size_t)nq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx, true);
+}
+
+
+int sd_band_depth_batched_f64(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_t ld,
+                              const uint8_t *membership, int64_t B, const int64_t *queries, int64_t nqb, int j,
+                              int relax, int64_t *count_out) {
+    SD_TRY(check_common(ctx, X, count_out, "sd_band_depth_batched_f64"));
+    SD_REQUIRE(membership && queries, "sd_band_depth_batched_f64: NULL membership/queries");
+    SD_REQUIRE(T >= 1 && n >= 1 && B >= 0 && nqb >= 1 && ld >= n, "sd_band_depth_batched_f64: bad sizes");
+    // host side: member lists and query positions inside each batch
+    std::vector<i64> cols, offs((size_t)B + 1, 0), qloc((size_t)(B * nqb));
+    std::vector<i64> pos((size_t)n);
+    for (i64 b = 0; b < B; ++b) {
+        const uint8_t *mb = membership + b * n;
+        i64 m = 0;
+        for (i64 c = 0; c < n; ++c) {
+            pos[(size_t)c] = -1;
+            if (mb[c]) {
+                pos[(size_t)c] = m++;
+                cols.push_back(c);
+            }
+        }
+        offs[(size_t)b + 1] = offs[(size_t)b] + m;
+        for (i64 i = 0; i < nqb; ++i) {
+            const i64 g = queries[b * nqb + i];
+            SD_REQUIRE(g >= 0 && g < n && pos[(size_t)g] >= 0,
+                       "sd_band_depth_batched_f64: query %lld of batch %lld is not a member", (long long)g,
+                       (long long)b);
+            qloc[(size_t)(b * nqb + i)] = pos[(size_t)g];
+        }
+    }
+    SD_TRY(begin_call(ctx));
+    double *dX = nullptr;
+    SD_TRY(upload_matrix(ctx, BUF_IN, X, T, n, ld, &dX));
+    SD_TRY(ctx->buf[BUF_AUX].reserve((cols.size() + 1) * sizeof(i64)));
+    SD_TRY(ctx->buf[BUF_MISC].reserve((qloc.size() + 1) * sizeof(i64)));
+    SD_TRY(ctx->buf[BUF_OUT].reserve((qloc.size() + 1) * sizeof(i64)));
+    SD_TRY(ctx->buf[BUF_IN2].reserve((size_t)T * n * sizeof(double)));
+    i64 *d_cols = ctx->buf[BUF_AUX].as<i64>();
+    i64 *d_ql = ctx->buf[BUF_MISC].as<i64>();
+    i64 *d_out = ctx->buf[BUF_OUT].as<i64>();
+    double *dXb = ctx->buf[BUF_IN2].as<double>();
+    if (!cols.empty())
+        SD_CUDA(cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
+    if (!qloc.empty())
+        SD_CUDA(cudaMemcpyAsync(d_ql, qloc.data(), qloc.size() * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
+    SD_TRY(mark(ctx, 1));
+    for (i64 b = 0; b < B; ++b) {
+        const i64 m = offs[(size_t)b + 1] - offs[(size_t)b];
+        SD_TRY(compact_columns_device(ctx, dX, T, n, d_cols + offs[(size_t)b], m, dXb));
+        SD_TRY(band_depth_device(ctx, dXb, T, m, m, d_ql + b * nqb, nqb, j, relax, d_out + b * nqb));
+    }
+    SD_TRY(mark(ctx, 2));
+    if (!qloc.empty())
+        SD_CUDA(cudaMemcpyAsync(count_out, d_out, qloc.size() * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
+    // cols / qloc are pageable host vectors: the async copies above were staged synchronously
+    return end_call(ctx, true);
+}
+
+}  // extern "C"

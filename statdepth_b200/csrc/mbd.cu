@@ -1,0 +1,552 @@
+// mbd.cu -- modified band depth (relax=True): per-time-row strict ranks on sm_100a.
+//
+// Replaces the relaxed branch of _r2_containment (statdepth/depth/calculations/_containment.py:68-80)
+// summed over all j-subsets by _univariate_band_depth (_functional.py:238-253).  For one time row,
+// with b / a = number of OTHER curves strictly below / above curve c,
+//     #{j-subsets whose closed band contains c} = C(n-1,j) - C(b,j) - C(a,j)
+// so the whole relaxed numerator is a per-row ranking problem (kernel "K1").
+//
+// Pipeline per block of time rows (all kernels on ctx->stream, no host sync):
+//   1. mbd_splitters_kernel : one CTA per row sorts a strided sample in shared memory (bitonic)
+//                             and emits P-1 equal-mass splitter VALUES.
+//   2. mbd_partition_kernel : streams the row once from HBM, binary-searches the splitters and
+//                             appends (value, curve id) to the part's slot list (fixed capacity CAP,
+//                             one global atomic per element).  Equal values always share a part, so
+//                             tie runs never straddle parts.
+//   3. mbd_rank_kernel      : ONE WARP per (row, part): loads <= CAP values, maps them to a 22-bit
+//                             monotone key packed with the slot id, sorts the packed u32 keys in
+//                             registers with a shuffle bitonic network, resolves equal-key runs with
+//                             exact fp64 compares, and adds term(b, a) to acc[curve] with a 64-bit RED.
+//   4. mbd_fallback_kernel  : rows in which some part overflowed CAP (heavy ties, adversarial
+//                             distributions) are ranked by a generic one-CTA-per-row bitonic sort of
+//                             order-preserving u64 keys + binary-search ranks.  Correct for any
+//                             finite input; ~3x slower.
+// HBM layout: X[t*ld + c] float64 (time-major rows are contiguous and streamed with coalesced
+// loads); acc int64[n]; part lists [row][part][CAP] float64 + uint32.
+#include "common.cuh"
+
+namespace sd {
+
+constexpr int CAP = 1024;          // slots per part == max elements one warp ranks
+constexpr int TARGET_PART = 400;   // mean part size the splitter count aims for
+constexpr int MAX_PARTS = 1024;
+constexpr int MAX_SAMPLE = 8192;   // 64 KB of shared memory in the splitter kernel
+constexpr int OVERSAMPLE = 32;     // sample elements per part
+constexpr int KEY_BITS = 22;       // reduced key bits (10 low bits carry the slot id)
+constexpr u32 KEY_MAX = (1u << KEY_BITS) - 1u;
+constexpr int PART_CHUNK = 16384;  // elements of one row handled by one partition CTA
+constexpr int FB_TILE = 4096;      // keys sorted in shared memory by the fallback
+
+__device__ __forceinline__ i64 comb2_dev(i64 m) { return m * (m - 1) / 2; }
+__device__ __forceinline__ i64 comb3_dev(i64 m) {
+    // m(m-1)/2 is exact; (m(m-1)/2)*(m-2) is divisible by 3; fits in int64 for m < 2.6e6
+    return m < 3 ? 0 : (m * (m - 1) / 2) * (m - 2) / 3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. splitters
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) mbd_splitters_kernel(const double *__restrict__ X, i64 n, i64 ld,
+                                                            int P, int S, double *__restrict__ splitters,
+                                                            int *__restrict__ status) {
+    extern __shared__ double smp[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double *xr = X + (i64)blockIdx.x * ld;
+    bool bad = false;
+    // strided sample taken in quads of 4 consecutive values (one 32 B sector each)
+    const i64 nquad = n >> 2;
+    const int squad = S >> 2;
+    for (int i = tid; i < S; i += nt) {
+        const i64 idx = (nquad >= squad && squad > 0) ? (((i64)(i >> 2) * nquad) / squad) * 4 + (i & 3)
+                                                       : ((i64)i * n) / S;
+        const double v = xr[idx];
+        bad |= !isfinite(v);
+        smp[i] = v;
+    }
+    if (bad) atomicOr(status, ST_NONFINITE);
+    __syncthreads();
+    // bitonic sort, "always ascending" form: first stage of each merge mirrors (e ^ (k-1)), the rest e ^ j
+    for (int k = 2; k <= S; k <<= 1) {
+        const int hk = k >> 1;
+        for (int i = tid; i < (S >> 1); i += nt) {
+            const int blk = i / hk, off = i - blk * hk;
+            const int a = blk * k + off, b = blk * k + k - 1 - off;
+            const double va = smp[a], vb = smp[b];
+            if (va > vb) { smp[a] = vb; smp[b] = va; }
+        }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int i = tid; i < (S >> 1); i += nt) {
+                const int a = 2 * j * (i / j) + (i % j), b = a + j;
+                const double va = smp[a], vb = smp[b];
+                if (va > vb) { smp[a] = vb; smp[b] = va; }
+            }
+            __syncthreads();
+        }
+    }
+    double *out = splitters + (i64)blockIdx.x * (P - 1);
+    for (int p = tid + 1; p < P; p += nt) out[p - 1] = smp[((i64)p * S) / P];
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. partition
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mbd_partition_kernel(const double *__restrict__ X, i64 n, i64 ld, int P,
+                                                            const double *__restrict__ splitters,
+                                                            int *__restrict__ cursor, int *__restrict__ rowflag,
+                                                            double *__restrict__ part_x, u32 *__restrict__ part_j,
+                                                            i64 row_stride, int *__restrict__ status) {
+    __shared__ double spl[MAX_PARTS];
+    const int row = blockIdx.y;
+    const double *xr = X + (i64)row * ld;
+    const int nspl = P - 1;
+    for (int i = threadIdx.x; i < nspl; i += blockDim.x) spl[i] = splitters[(i64)row * nspl + i];
+    __syncthreads();
+    int top = 1;
+    while (top < P) top <<= 1;  // power of two >= P  (> nspl)
+    const i64 c0 = (i64)blockIdx.x * PART_CHUNK;
+    const i64 c1 = c0 + PART_CHUNK < n ? c0 + PART_CHUNK : n;
+    double *px = part_x + (i64)row * row_stride;
+    u32 *pj = part_j + (i64)row * row_stride;
+    int *cur = cursor + (i64)row * P;
+    bool bad = false, over = false;
+    for (i64 c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+        const double x = xr[c];
+        bad |= !isfinite(x);
+        // part = number of splitters <= x  (upper bound), branch-free
+        int lo = 0;
+        for (int step = top >> 1; step > 0; step >>= 1) {
+            const int probe = lo + step;
+            if (probe <= nspl && spl[probe - 1] <= x) lo = probe;
+        }
+        const int slot = atomicAdd(&cur[lo], 1);
+        if (slot < CAP) {
+            const i64 at = (i64)lo * CAP + slot;
+            px[at] = x;
+            pj[at] = (u32)c;
+        } else {
+            over = true;
+        }
+    }
+    if (bad) atomicOr(status, ST_NONFINITE);
+    if (over) rowflag[row] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. per-part warp ranking
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ce_u32(u32 &a, u32 &b) {
+    const u32 lo = min(a, b), hi = max(a, b);
+    a = lo;
+    b = hi;
+}
+
+// sorts 32*EPL keys held as v[i] at element index e = lane*EPL + i, ascending in e
+template <int EPL>
+__device__ __forceinline__ void warp_bitonic_sort(u32 (&v)[EPL], const int lane) {
+    constexpr int N = 32 * EPL;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+        if (k <= EPL) {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                const int p = i ^ (k - 1);
+                if (i < p) ce_u32(v[i], v[p]);
+            }
+        } else {
+            const int lm = k / EPL - 1;
+            const bool lower = (lane & ((k / EPL) >> 1)) == 0;
+            u32 o[EPL];
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) o[i] = __shfl_xor_sync(0xffffffffu, v[EPL - 1 - i], lm);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) v[i] = lower ? min(v[i], o[i]) : max(v[i], o[i]);
+        }
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            if (j < EPL) {
+#pragma unroll
+                for (int i = 0; i < EPL; ++i)
+                    if ((i & j) == 0) ce_u32(v[i], v[i | j]);
+            } else {
+                const int lm = j / EPL;
+                const bool lower = (lane & lm) == 0;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) {
+                    const u32 o = __shfl_xor_sync(0xffffffffu, v[i], lm);
+                    v[i] = lower ? min(v[i], o) : max(v[i], o);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, s));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
+    return v;
+}
+
+struct RankOut {
+    i64 *acc2, *acc3;      // acc3 may be null
+    int *rank_b, *rank_a;  // may be null; [row_global*n + c]
+    i64 n;
+    i64 full2, full3;      // C(n-1,2), C(n-1,3)
+};
+
+__device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, u32 c, i64 b, i64 a) {
+    atomicAdd((u64 *)&o.acc2[c], (u64)(o.full2 - comb2_dev(b) - comb2_dev(a)));
+    if (o.acc3) atomicAdd((u64 *)&o.acc3[c], (u64)(o.full3 - comb3_dev(b) - comb3_dev(a)));
+    if (o.rank_b) {
+        o.rank_b[row_global * o.n + c] = (int)b;
+        o.rank_a[row_global * o.n + c] = (int)a;
+    }
+}
+
+// skeys / sres: this warp's shared scratch (CAP words each)
+template <int EPL>
+__device__ __forceinline__ void rank_part(const double *__restrict__ px, const u32 *__restrict__ pj, const int cnt,
+                                          const i64 base, const i64 row_global, const RankOut &o, u32 *skeys,
+                                          u32 *sres, const int lane) {
+    // pass 1: range of the part
+    double lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const int s = lane + 32 * k;
+        if (s < cnt) {
+            const double x = px[s];
+            lo = fmin(lo, x);
+            hi = fmax(hi, x);
+        }
+    }
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    if (lo == hi) {  // every element ties: b = everything in lower parts, a = everything in higher parts
+        const i64 b = base, a = o.n - base - cnt;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            const int s = lane + 32 * k;
+            if (s < cnt) emit_rank(o, row_global, pj[s], b, a);
+        }
+        return;
+    }
+    // pass 2: monotone 22-bit key | slot id.  x >= lo exactly, every step below is monotone in x.
+    const double scale = (double)KEY_MAX / (hi - lo);
+    u32 v[EPL];
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const int s = lane + 32 * k;
+        u32 key = 0xffffffffu;
+        if (s < cnt) {
+            const double t = (px[s] - lo) * scale;
+            u32 r = (u32)__double2uint_rz(t);  // NaN (inf*0) converts to 0: still consistent, resolved by the run scan
+            r = min(r, KEY_MAX);
+            key = (r << 10) | (u32)s;
+        }
+        v[k] = key;
+    }
+    warp_bitonic_sort<EPL>(v, lane);
+    // sorted position pos = lane*EPL + i lives at skeys[i*32 + lane] (conflict-free)
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) skeys[i * 32 + lane] = v[i];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const int pos = lane * EPL + i;
+        if (pos < cnt) {
+            const u32 key = v[i];
+            const u32 r = key >> 10;
+            const int slot = (int)(key & 1023u);
+            int rs = pos, re = pos + 1, less = 0, greater = 0;
+            double xs = 0.0;
+            bool have = false;
+            for (int m = pos - 1; m >= 0; --m) {  // equal-key run to the left (normally empty)
+                const u32 km = skeys[(m % EPL) * 32 + m / EPL];
+                if ((km >> 10) != r) break;
+                if (!have) { xs = px[slot]; have = true; }
+                const double xm = px[km & 1023u];
+                less += xm < xs;
+                greater += xm > xs;
+                rs = m;
+            }
+            for (int m = pos + 1; m < cnt; ++m) {  // ... and to the right
+                const u32 km = skeys[(m % EPL) * 32 + m / EPL];
+                if ((km >> 10) != r) break;
+                if (!have) { xs = px[slot]; have = true; }
+                const double xm = px[km & 1023u];
+                less += xm < xs;
+                greater += xm > xs;
+                re = m + 1;
+            }
+            sres[slot] = (u32)(rs + less) | ((u32)(re - greater) << 16);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const int s = lane + 32 * k;
+        if (s < cnt) {
+            const u32 res = sres[s];
+            const i64 b = base + (i64)(res & 0xffffu);
+            const i64 a = o.n - base - (i64)(res >> 16);
+            emit_rank(o, row_global, pj[s], b, a);
+        }
+    }
+    __syncwarp();
+}
+
+constexpr int RANK_WARPS = 4;  // 2 x 4 KB of shared scratch per warp -> 32 KB static per CTA
+
+__global__ void __launch_bounds__(RANK_WARPS * 32) mbd_rank_kernel(const int P, const i64 nwarps,
+                                                                   const int *__restrict__ cursor,
+                                                                   const int *__restrict__ rowflag,
+                                                                   const double *__restrict__ part_x,
+                                                                   const u32 *__restrict__ part_j,
+                                                                   const i64 row_stride, const i64 row0,
+                                                                   const RankOut o) {
+    __shared__ u32 s_keys[RANK_WARPS][CAP];
+    __shared__ u32 s_res[RANK_WARPS][CAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const i64 w = (i64)blockIdx.x * RANK_WARPS + wid;
+    if (w >= nwarps) return;
+    const i64 row = w / P;
+    const int part = (int)(w - row * P);
+    if (rowflag[row]) return;  // the whole row goes to the generic path
+    const int *cur = cursor + row * P;
+    const int cnt = cur[part];
+    if (cnt == 0) return;
+    i64 base = 0;
+    for (int p = lane; p < part; p += 32) base += cur[p];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) base += __shfl_xor_sync(0xffffffffu, base, s);
+    const double *px = part_x + row * row_stride + (i64)part * CAP;
+    const u32 *pj = part_j + row * row_stride + (i64)part * CAP;
+    if (cnt <= 128) rank_part<4>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
+    else if (cnt <= 256) rank_part<8>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
+    else if (cnt <= 512) rank_part<16>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
+    else rank_part<32>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. generic path: one CTA ranks one row (any finite input, any tie structure)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ce_u64(u64 &a, u64 &b) {
+    if (a > b) { const u64 t = a; a = b; b = t; }
+}
+
+// sorts tile[0..len) (len power of two <= FB_TILE) ascending; all threads of the CTA participate
+__device__ void smem_sort_full(u64 *tile, int len) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int k = 2; k <= len; k <<= 1) {
+        const int hk = k >> 1;
+        for (int i = tid; i < (len >> 1); i += nt) {
+            const int blk = i / hk, off = i - blk * hk;
+            ce_u64(tile[blk * k + off], tile[blk * k + k - 1 - off]);
+        }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int i = tid; i < (len >> 1); i += nt) {
+                const int a = 2 * j * (i / j) + (i % j);
+                ce_u64(tile[a], tile[a + j]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// finishes a merge inside a tile: stages j = len/2 .. 1
+__device__ void smem_merge_tail(u64 *tile, int len) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = len >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < (len >> 1); i += nt) {
+            const int a = 2 * j * (i / j) + (i % j);
+            ce_u64(tile[a], tile[a + j]);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) mbd_fallback_kernel(const double *__restrict__ X, const i64 n, const i64 ld,
+                                                             const i64 NP, const int *__restrict__ rowflag,
+                                                             u64 *__restrict__ scratch, const i64 row_stride,
+                                                             const i64 row0, const RankOut o,
+                                                             int *__restrict__ status, int *__restrict__ fb_count) {
+    __shared__ u64 tile[FB_TILE];
+    const i64 row = blockIdx.x;
+    if (!rowflag[row]) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) atomicAdd(fb_count, 1);
+    const double *xr = X + row * ld;
+    u64 *keys = scratch + row * row_stride;
+    bool bad = false;
+    for (i64 c = tid; c < NP; c += nt) {
+        u64 k = ~0ull;
+        if (c < n) {
+            const double x = xr[c];
+            bad |= !isfinite(x);
+            k = sortable_key(x);
+        }
+        keys[c] = k;
+    }
+    if (bad) atomicOr(status, ST_NONFINITE);
+    __syncthreads();
+    const int tl = NP < FB_TILE ? (int)NP : FB_TILE;
+    for (i64 t0 = 0; t0 < NP; t0 += tl) {  // sort every tile in shared memory
+        for (int i = tid; i < tl; i += nt) tile[i] = keys[t0 + i];
+        __syncthreads();
+        smem_sort_full(tile, tl);
+        for (int i = tid; i < tl; i += nt) keys[t0 + i] = tile[i];
+        __syncthreads();
+    }
+    for (i64 k = 2 * (i64)tl; k <= NP; k <<= 1) {  // merges wider than a tile: global stages, then tile tails
+        const i64 hk = k >> 1;
+        for (i64 i = tid; i < (NP >> 1); i += nt) {
+            const i64 blk = i / hk, off = i - blk * hk;
+            const i64 a = blk * k + off, b = blk * k + k - 1 - off;
+            u64 va = keys[a], vb = keys[b];
+            if (va > vb) { keys[a] = vb; keys[b] = va; }
+        }
+        __syncthreads();
+        for (i64 j = k >> 2; j >= tl; j >>= 1) {
+            for (i64 i = tid; i < (NP >> 1); i += nt) {
+                const i64 a = 2 * j * (i / j) + (i % j), b = a + j;
+                u64 va = keys[a], vb = keys[b];
+                if (va > vb) { keys[a] = vb; keys[b] = va; }
+            }
+            __syncthreads();
+        }
+        for (i64 t0 = 0; t0 < NP; t0 += tl) {
+            for (int i = tid; i < tl; i += nt) tile[i] = keys[t0 + i];
+            __syncthreads();
+            smem_merge_tail(tile, tl);
+            for (int i = tid; i < tl; i += nt) keys[t0 + i] = tile[i];
+            __syncthreads();
+        }
+    }
+    // ranks by binary search in the sorted keys (first n entries are the real ones)
+    for (i64 c = tid; c < n; c += nt) {
+        const u64 key = sortable_key(xr[c]);
+        i64 lo = 0, hi = n;  // lower bound: first index with keys[idx] >= key
+        while (lo < hi) {
+            const i64 mid = (lo + hi) >> 1;
+            if (keys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        const i64 b = lo;
+        hi = n;  // upper bound: first index with keys[idx] > key (starts at lo)
+        while (lo < hi) {
+            const i64 mid = (lo + hi) >> 1;
+            if (keys[mid] <= key) lo = mid + 1; else hi = mid;
+        }
+        emit_rank(o, row0 + row, (u32)c, b, n - lo);
+    }
+}
+
+__global__ void fill_int_kernel(int *p, i64 count, int value) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) p[i] = value;
+}
+
+// ---------------------------------------------------------------------------------------------
+// driver
+// ---------------------------------------------------------------------------------------------
+static int pow2ceil_int(i64 v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Sum over ALL curves of one matrix: d_acc2[c] (and d_acc3[c]) += sum_t term_j(b,a).  The
+// accumulators are zeroed here.  Optional per-(t,c) rank output.
+int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool want_j3, i64 *d_acc2, i64 *d_acc3,
+                   int *d_rank_b, int *d_rank_a) {
+    if (n < 1 || T < 0 || ld < n) {
+        set_error("mbd: bad shape T=%lld n=%lld ld=%lld", (long long)T, (long long)n, (long long)ld);
+        return SD_ERR_INVALID;
+    }
+    if (n >= (1ll << 31)) {
+        set_error("mbd: n=%lld exceeds 2^31-1", (long long)n);
+        return SD_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = ctx->stream;
+    SD_CUDA(cudaMemsetAsync(d_acc2, 0, (size_t)n * sizeof(i64), st));
+    if (want_j3) SD_CUDA(cudaMemsetAsync(d_acc3, 0, (size_t)n * sizeof(i64), st));
+    if (T == 0) return SD_OK;
+
+    int P = n <= 512 ? 1 : (int)ceil_div(n, TARGET_PART);
+    if (P > MAX_PARTS) P = MAX_PARTS;
+    int S = 0;
+    if (P > 1) {
+        S = pow2ceil_int((i64)OVERSAMPLE * P);
+        if (S > MAX_SAMPLE) S = MAX_SAMPLE;
+        while (S > n) S >>= 1;
+    }
+    const i64 NP = pow2ceil_int(n);
+    const i64 row_stride = (i64)P * CAP > NP ? (i64)P * CAP : NP;  // 8-byte slots per row
+
+    // rows per block: keep the part lists within ~6 GB
+    const size_t per_row = (size_t)row_stride * 12;
+    i64 Tc = (i64)((6ull << 30) / per_row);
+    if (Tc < 1) Tc = 1;
+    if (Tc > T) Tc = T;
+    if (Tc > 65535) Tc = 65535;
+
+    SD_TRY(ctx->buf[BUF_PART_X].reserve((size_t)Tc * row_stride * 8));
+    SD_TRY(ctx->buf[BUF_PART_J].reserve((size_t)Tc * row_stride * 4));
+    SD_TRY(ctx->buf[BUF_CURSOR].reserve((size_t)Tc * (P + 1) * sizeof(int)));
+    SD_TRY(ctx->buf[BUF_SPLIT].reserve((size_t)Tc * (P > 1 ? P - 1 : 1) * sizeof(double)));
+    double *part_x = ctx->buf[BUF_PART_X].as<double>();
+    u32 *part_j = ctx->buf[BUF_PART_J].as<u32>();
+    int *cursor = ctx->buf[BUF_CURSOR].as<int>();
+    int *rowflag = cursor + (size_t)Tc * P;
+    double *splitters = ctx->buf[BUF_SPLIT].as<double>();
+    int *fb_count = ctx->d_status + 1;
+
+    SD_CUDA(cudaFuncSetAttribute(mbd_splitters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 MAX_SAMPLE * (int)sizeof(double)));
+
+    RankOut o;
+    o.acc2 = d_acc2;
+    o.acc3 = want_j3 ? d_acc3 : nullptr;
+    o.rank_b = d_rank_b;
+    o.rank_a = d_rank_a;
+    o.n = n;
+    o.full2 = (n - 1) * (n - 2) / 2;
+    o.full3 = n - 1 < 3 ? 0 : ((n - 1) * (n - 2) / 2) * (n - 3) / 3;
+
+    for (i64 r0 = 0; r0 < T; r0 += Tc) {
+        const i64 rows = T - r0 < Tc ? T - r0 : Tc;
+        const double *Xb = dX + r0 * ld;
+        if (ctx->mbd_force_fallback) {
+            fill_int_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(rowflag, rows, 1);
+            ctx->last.launches++;
+        } else {
+            SD_CUDA(cudaMemsetAsync(cursor, 0, (size_t)Tc * (P + 1) * sizeof(int), st));
+            if (P > 1) {
+                mbd_splitters_kernel<<<(unsigned)rows, 512, (size_t)S * sizeof(double), st>>>(
+                    Xb, n, ld, P, S, splitters, ctx->d_status);
+                ctx->last.launches++;
+            }
+            dim3 pgrid((unsigned)ceil_div(n, PART_CHUNK), (unsigned)rows);
+            mbd_partition_kernel<<<pgrid, 256, 0, st>>>(Xb, n, ld, P, splitters, cursor, rowflag, part_x, part_j,
+                                                        row_stride, ctx->d_status);
+            ctx->last.launches++;
+            const i64 nwarps = rows * P;
+            mbd_rank_kernel<<<(unsigned)ceil_div(nwarps, RANK_WARPS), RANK_WARPS * 32, 0, st>>>(
+                P, nwarps, cursor, rowflag, part_x, part_j, row_stride, r0, o);
+            ctx->last.launches++;
+        }
+        // rows flagged as overflowing (or all rows when forced): generic path; idle CTAs exit at once
+        mbd_fallback_kernel<<<(unsigned)rows, 1024, 0, st>>>(Xb, n, ld, NP, rowflag, (u64 *)part_x, row_stride, r0, o,
+                                                             ctx->d_status, fb_count);
+        ctx->last.launches++;
+        SD_CUDA(cudaGetLastError());
+    }
+    return SD_OK;
+}
+
+}  // namespace sd

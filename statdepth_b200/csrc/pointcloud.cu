@@ -1,0 +1,313 @@
+// pointcloud.cu -- point-cloud depths: L1, simplicial (brute-force, exact predicate), Oja; and the
+// multivariate functional simplex depth, which shares the simplex predicate.
+//
+// Reference routines replaced (statdepth/depth/calculations/):
+//   _L1_depth            _pointcloud.py:125-150
+//   _pointwisedepth      _pointcloud.py:44-56   ('simplex' branch: all (d+1)-subsets of the others)
+//   _oja_depth           _pointcloud.py:176-204
+//   _simplex_depth       _functional.py:257-286 + _simplex_containment _containment.py:105-136
+// Compiled with -fmad=false: see simplex_pred.cuh.
+#include "common.cuh"
+#include "simplex_pred.cuh"
+
+namespace sd {
+
+// ---------------------------------------------------------------------------------------------
+// L1 depth: one thread per query point, all points streamed through shared memory, float64
+// accumulation in index order (the order of the reference's Python loop, _pointcloud.py:145-146)
+// ---------------------------------------------------------------------------------------------
+constexpr int L1_TILE = 512;
+constexpr int L1_MAXD = 16;
+
+template <int D>
+__global__ void __launch_bounds__(128) l1_kernel(const double *__restrict__ P, const i64 n, const int d_rt,
+                                                 const i64 *__restrict__ q, const i64 nq,
+                                                 double *__restrict__ out) {
+    extern __shared__ double s_pts[];  // L1_TILE * d
+    const int d = D > 0 ? D : d_rt;
+    const i64 qi = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = qi < nq;
+    const i64 p = active ? (q ? q[qi] : qi) : 0;
+    double xp[D > 0 ? D : L1_MAXD], s[D > 0 ? D : L1_MAXD];
+#pragma unroll
+    for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c) {
+        xp[c] = (c < d) ? P[p * d + c] : 0.0;
+        s[c] = 0.0;
+    }
+    for (i64 t0 = 0; t0 < n; t0 += L1_TILE) {
+        const int len = (n - t0) < L1_TILE ? (int)(n - t0) : L1_TILE;
+        __syncthreads();
+        for (int i = threadIdx.x; i < len * d; i += blockDim.x) s_pts[i] = P[t0 * d + i];
+        __syncthreads();
+        if (active) {
+            for (int o = 0; o < len; ++o) {
+                if (t0 + o == p) continue;
+                double nrm2 = 0.0, diff[D > 0 ? D : L1_MAXD];
+#pragma unroll
+                for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c) {
+                    if (c < d) {
+                        const double xo = s_pts[o * d + c];
+                        diff[c] = xo - xp[c];
+                        const double back = xp[c] - xo;
+                        nrm2 += back * back;
+                    }
+                }
+                const double nrm = sqrt(nrm2);
+#pragma unroll
+                for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c)
+                    if (c < d) s[c] += diff[c] / nrm;
+            }
+        }
+    }
+    if (active) {
+        double tot = 0.0;
+#pragma unroll
+        for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c)
+            if (c < d) tot += s[c] * s[c];
+        out[qi] = 1.0 - sqrt(tot) / (double)n;
+    }
+}
+
+int l1_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 nq, double *d_out) {
+    if (nq == 0) return SD_OK;
+    const unsigned grid = (unsigned)ceil_div(nq, 128);
+    const size_t smem = (size_t)L1_TILE * d * sizeof(double);
+    cudaStream_t st = ctx->stream;
+    switch (d) {
+        case 1: l1_kernel<1><<<grid, 128, smem, st>>>(dP, n, d, d_q, nq, d_out); break;
+        case 2: l1_kernel<2><<<grid, 128, smem, st>>>(dP, n, d, d_q, nq, d_out); break;
+        case 3: l1_kernel<3><<<grid, 128, smem, st>>>(dP, n, d, d_q, nq, d_out); break;
+        default:
+            SD_CUDA(cudaFuncSetAttribute(l1_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L1_TILE * L1_MAXD * (int)sizeof(double)));
+            l1_kernel<0><<<grid, 128, smem, st>>>(dP, n, d, d_q, nq, d_out);
+            break;
+    }
+    ctx->last.launches++;
+    SD_CUDA(cudaGetLastError());
+    return SD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers: pair unranking and block reductions
+// ---------------------------------------------------------------------------------------------
+// pid in [0, m(m-1)/2) -> (a < b), pid = b(b-1)/2 + a
+__device__ __forceinline__ void unrank_pair(const i64 pid, i64 &a, i64 &b) {
+    b = (i64)((1.0 + sqrt(1.0 + 8.0 * (double)pid)) * 0.5);
+    while (b * (b - 1) / 2 > pid) --b;
+    while ((b + 1) * b / 2 <= pid) ++b;
+    a = pid - b * (b - 1) / 2;
+}
+
+__device__ __forceinline__ u64 block_sum_u64(u64 v, u64 *s_scratch) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_scratch[wid] = v;
+    __syncthreads();
+    u64 tot = 0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) tot += s_scratch[w];
+    return tot;  // valid on thread 0
+}
+
+__device__ __forceinline__ double block_sum_f64(double v, double *s_scratch) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_scratch[wid] = v;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) tot += s_scratch[w];
+    return tot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// simplicial depth numerator: one CTA per query point, threads stride over pairs of the other
+// points (positions in the "others" list skip the query), inner loops add the remaining vertices
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) simplicial_kernel(const double *__restrict__ P, const i64 n,
+                                                         const i64 *__restrict__ q, const double tol,
+                                                         i64 *__restrict__ out) {
+    __shared__ u64 s_red[8];
+    const i64 p = q ? q[blockIdx.x] : (i64)blockIdx.x;
+    const i64 m = n - 1;  // others
+    double xp[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) xp[c] = P[p * D + c];
+    u64 count = 0;
+    const i64 npairs = m * (m - 1) / 2;
+    for (i64 pid = threadIdx.x; pid < npairs; pid += blockDim.x) {
+        i64 ia, ib;
+        unrank_pair(pid, ia, ib);
+        const i64 a = ia + (ia >= p), b = ib + (ib >= p);
+        double V[(D + 1) * D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            V[c] = P[a * D + c];
+            V[D + c] = P[b * D + c];
+        }
+        if (D == 1) {
+            count += in_simplex<D>(V, xp, tol);
+        } else {
+            for (i64 ic = ib + 1; ic < m; ++ic) {
+                const i64 c3 = ic + (ic >= p);
+#pragma unroll
+                for (int c = 0; c < D; ++c) V[2 * D + c] = P[c3 * D + c];
+                if (D == 2) {
+                    count += in_simplex<D>(V, xp, tol);
+                } else {
+                    for (i64 ie = ic + 1; ie < m; ++ie) {
+                        const i64 c4 = ie + (ie >= p);
+#pragma unroll
+                        for (int c = 0; c < D; ++c) V[3 * D + c] = P[c4 * D + c];
+                        count += in_simplex<D>(V, xp, tol);
+                    }
+                }
+            }
+        }
+    }
+    const u64 tot = block_sum_u64(count, s_red);
+    if (threadIdx.x == 0) out[blockIdx.x] = (i64)tot;
+}
+
+int simplicial_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 nq, double tol,
+                      i64 *d_out) {
+    if (nq == 0) return SD_OK;
+    cudaStream_t st = ctx->stream;
+    const unsigned grid = (unsigned)nq;
+    switch (d) {
+        case 1: simplicial_kernel<1><<<grid, 256, 0, st>>>(dP, n, d_q, tol, d_out); break;
+        case 2: simplicial_kernel<2><<<grid, 256, 0, st>>>(dP, n, d_q, tol, d_out); break;
+        case 3: simplicial_kernel<3><<<grid, 256, 0, st>>>(dP, n, d_q, tol, d_out); break;
+        default: set_error("simplicial depth: d=%d not supported", d); return SD_ERR_UNSUPPORTED;
+    }
+    ctx->last.launches++;
+    SD_CUDA(cudaGetLastError());
+    return SD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Oja: sum over d-subsets of pool \ {p} of |det| / d!
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) oja_kernel(const double *__restrict__ P, const i64 *__restrict__ q,
+                                                  const i64 *__restrict__ pool, const i64 npool,
+                                                  const double hull_volume, double *__restrict__ out) {
+    __shared__ double s_red[8];
+    const i64 p = q ? q[blockIdx.x] : (i64)blockIdx.x;
+    double xp[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) xp[c] = P[p * D + c];
+    double acc = 0.0;
+    const i64 npairs = npool * (npool - 1) / 2;
+    for (i64 pid = threadIdx.x; pid < npairs; pid += blockDim.x) {
+        i64 ia, ib;
+        unrank_pair(pid, ia, ib);
+        const i64 a = pool ? pool[ia] : ia, b = pool ? pool[ib] : ib;
+        if (a == p || b == p) continue;
+        if (D == 2) {
+            acc += fabs(orient2(P + a * 2, P + b * 2, xp)) / 2.0;
+        } else {
+            for (i64 ic = ib + 1; ic < npool; ++ic) {
+                const i64 c3 = pool ? pool[ic] : ic;
+                if (c3 == p) continue;
+                acc += fabs(orient3(P + a * 3, P + b * 3, P + c3 * 3, xp)) / 6.0;
+            }
+        }
+    }
+    const double tot = block_sum_f64(acc, s_red);
+    if (threadIdx.x == 0) out[blockIdx.x] = tot / hull_volume;
+}
+
+int oja_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 nq, const i64 *d_pool, i64 npool,
+               double hull_volume, double *d_out) {
+    (void)n;
+    if (nq == 0) return SD_OK;
+    cudaStream_t st = ctx->stream;
+    if (d == 2) oja_kernel<2><<<(unsigned)nq, 256, 0, st>>>(dP, d_q, d_pool, npool, hull_volume, d_out);
+    else if (d == 3) oja_kernel<3><<<(unsigned)nq, 256, 0, st>>>(dP, d_q, d_pool, npool, hull_volume, d_out);
+    else { set_error("oja: d=%d not supported", d); return SD_ERR_UNSUPPORTED; }
+    ctx->last.launches++;
+    SD_CUDA(cudaGetLastError());
+    return SD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multivariate functional simplex depth numerator: one CTA per query curve; F[(i*T + t)*D + c]
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ i64 subset_count(const double *__restrict__ F, const i64 T, const i64 qc, const i64 *o,
+                                            const bool relax, const double tol) {
+    i64 cnt = 0;
+    for (i64 t = 0; t < T; ++t) {
+        double V[(D + 1) * D], xp[D];
+#pragma unroll
+        for (int k = 0; k <= D; ++k)
+#pragma unroll
+            for (int c = 0; c < D; ++c) V[k * D + c] = F[(o[k] * T + t) * D + c];
+#pragma unroll
+        for (int c = 0; c < D; ++c) xp[c] = F[(qc * T + t) * D + c];
+        if (in_simplex<D>(V, xp, tol)) ++cnt;
+        else if (!relax) return 0;
+    }
+    return relax ? cnt : 1;  // strict: reached the end <=> contained at all T rows
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) simplex_depth_kernel(const double *__restrict__ F, const i64 N, const i64 T,
+                                                            const i64 *__restrict__ q, const int relax,
+                                                            const double tol, i64 *__restrict__ out) {
+    __shared__ u64 s_red[8];
+    const i64 qc = q ? q[blockIdx.x] : (i64)blockIdx.x;
+    const i64 m = N - 1;
+    u64 acc = 0;
+    const i64 npairs = m * (m - 1) / 2;
+    for (i64 pid = threadIdx.x; pid < npairs; pid += blockDim.x) {
+        i64 ia, ib;
+        unrank_pair(pid, ia, ib);
+        i64 o[4];
+        o[0] = ia + (ia >= qc);
+        o[1] = ib + (ib >= qc);
+        o[2] = o[3] = 0;
+        if (D == 1) {
+            acc += (u64)subset_count<D>(F, T, qc, o, relax != 0, tol);
+        } else {
+            for (i64 ic = ib + 1; ic < m; ++ic) {
+                o[2] = ic + (ic >= qc);
+                if (D == 2) {
+                    acc += (u64)subset_count<D>(F, T, qc, o, relax != 0, tol);
+                } else {
+                    for (i64 ie = ic + 1; ie < m; ++ie) {
+                        o[3] = ie + (ie >= qc);
+                        acc += (u64)subset_count<D>(F, T, qc, o, relax != 0, tol);
+                    }
+                }
+            }
+        }
+    }
+    const u64 tot = block_sum_u64(acc, s_red);
+    if (threadIdx.x == 0) out[blockIdx.x] = (i64)tot;
+}
+
+int simplex_depth_device(sd_ctx *ctx, const double *dF, i64 N, i64 T, int d, const i64 *d_q, i64 nq, int relax,
+                         double tol, i64 *d_out) {
+    if (nq == 0) return SD_OK;
+    cudaStream_t st = ctx->stream;
+    const unsigned grid = (unsigned)nq;
+    switch (d) {
+        case 1: simplex_depth_kernel<1><<<grid, 256, 0, st>>>(dF, N, T, d_q, relax, tol, d_out); break;
+        case 2: simplex_depth_kernel<2><<<grid, 256, 0, st>>>(dF, N, T, d_q, relax, tol, d_out); break;
+        case 3: simplex_depth_kernel<3><<<grid, 256, 0, st>>>(dF, N, T, d_q, relax, tol, d_out); break;
+        default: set_error("simplex depth: d=%d not supported", d); return SD_ERR_UNSUPPORTED;
+    }
+    ctx->last.launches++;
+    SD_CUDA(cudaGetLastError());
+    return SD_OK;
+}
+
+}  // namespace sd

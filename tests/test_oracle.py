@@ -1,0 +1,126 @@
+"""CPU: pin the oracle against the reference's golden vectors."""
+from math import comb
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle
+
+
+def _depth(counts_by_j, n, T, relax):
+    d = np.zeros(len(next(iter(counts_by_j.values()))))
+    for j, c in counts_by_j.items():
+        s = c.astype(np.float64)
+        if relax:
+            s = s / T
+        d = d + s / comb(n, j)
+    return d
+
+
+DOC_STRICT = {"f_3": 0.4, "f_5": 0.266667, "f_2": 0.2, "f_1": 0.2, "f_4": 0.0, "f_0": 0.0}
+
+
+def test_doc_example_band_depth(oracle, golden):
+    """docs/index.md:20-42 prints the strict J=2 depths of the 6x5 table."""
+    case = golden["doc_table_J2_strict"]
+    X = np.array(case["X"])
+    d = _depth({2: oracle.bd_counts(X)}, 6, 5, False)
+    for name, val in zip(case["columns"], d):
+        assert abs(val - DOC_STRICT[name]) < 5e-7
+    assert d.tolist() == case["depths"]
+
+
+def test_doc_example_l1(oracle, golden):
+    """docs/index.md:98-112 prints the L1 depths of 5 points (inputs are 6-digit roundings)."""
+    case = golden["doc_l1"]
+    d = oracle.l1_depth(np.array(case["P"]))
+    np.testing.assert_allclose(d, [0.703605, 0.239076, 0.458779, 0.456768, 0.258959], atol=2e-6)
+    np.testing.assert_allclose(d, case["depths"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["doc_table_J2_strict", "doc_table_J2_relax", "doc_table_J3_strict",
+                                  "doc_table_J3_relax", "walk_16x14_J2_strict", "walk_16x14_J2_relax",
+                                  "walk_16x14_J3_strict", "walk_16x14_J3_relax", "ties_12x13_strict",
+                                  "ties_12x13_relax", "generator_default_seed4"])
+def test_band_depth_vs_reference(oracle, golden, name):
+    case = golden[name]
+    X = np.array(case["X"])
+    T, n = X.shape
+    J, relax = case["kwargs"]["J"], case["kwargs"]["relax"]
+    closed, enum = {}, {}
+    for j in range(2, J + 1):
+        closed[j] = oracle.mbd_counts_all(X, j=j) if relax else oracle.bd_counts(X, j=j)
+        enum[j] = oracle.band_counts_enum(X, j=j, relax=relax)
+        assert (closed[j] == enum[j]).all()  # closed form == the reference's own enumeration
+    d = _depth(closed, n, T, relax)
+    if relax:
+        np.testing.assert_allclose(d, case["depths"], rtol=1e-12)
+    else:
+        assert d.tolist() == case["depths"]
+
+
+def test_cfg1_shape_vs_reference(oracle, golden):
+    """BASELINE config 1 (200 curves x 100 points): 2 query curves computed by the reference."""
+    X = np.random.default_rng(0).standard_normal((100, 200)).cumsum(0)
+    s = golden["cfg1_200x100_strict"]
+    d = oracle.bd_counts(X, s["to_compute"]).astype(np.float64) / comb(200, 2)
+    assert d.tolist() == s["depths"]
+    r = golden["cfg1_200x100_relax"]
+    d = oracle.mbd_counts_all(X)[r["to_compute"]].astype(np.float64) / 100 / comb(200, 2)
+    np.testing.assert_allclose(d, r["depths"], rtol=1e-12)
+
+
+def test_numpy_restatement_agrees(oracle):
+    rng = np.random.default_rng(5)
+    for X in (rng.standard_normal((20, 40)).cumsum(0), np.round(rng.standard_normal((9, 30)).cumsum(0))):
+        assert (np.array(np_oracle.mbd_counts(X, 2), dtype=np.int64) == oracle.mbd_counts_all(X)).all()
+        assert (np.array(np_oracle.mbd_counts(X, 3), dtype=np.int64) == oracle.mbd_counts_all(X, j=3)).all()
+        assert (np_oracle.bd_counts(X) == oracle.bd_counts(X)).all()
+        b, a = np_oracle.ranks(X)
+        _, rb, ra = oracle.mbd_counts_all(X, want_ranks=True)
+        assert (b == rb).all() and (a == ra).all()
+
+
+@pytest.mark.parametrize("name", ["generator_deg_seed0", "generator_deg_seed1", "generator_deg_seed2",
+                                  "generator_deg_seed3", "generator_deg_d2_relax", "walk_8x6x2_strict",
+                                  "walk_8x6x2_relax", "walk_7x4x3_relax"])
+def test_simplex_depth_vs_reference(oracle, golden, name):
+    case = golden[name]
+    F = np.array(case["F"])
+    N, T, d = F.shape
+    relax = case["kwargs"]["relax"]
+    c = oracle.simplex_depth_counts(F, relax=relax).astype(np.float64)
+    dep = (c / T if relax else c) / comb(N - 1, d + 1)
+    np.testing.assert_allclose(dep, case["depths"], rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["l1_15x2", "l1_12x3", "simplex_10x2", "simplex_9x3", "simplex_gen_seed2",
+                                  "oja_10x2", "oja_8x3"])
+def test_pointcloud_vs_reference(oracle, golden, name):
+    case = golden[name]
+    P = np.array(case["P"])
+    n, d = P.shape
+    if case["containment"] == "l1":
+        got = oracle.l1_depth(P)
+    elif case["containment"] == "simplex":
+        got = oracle.simplicial_counts(P).astype(np.float64) / comb(n, d + 1)
+    else:
+        got = oracle.oja(P, case["hull_volume"])
+    np.testing.assert_allclose(got, case["depths"], rtol=1e-12, atol=1e-15)
+
+
+def test_simplex_predicate_edges(oracle):
+    tri = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+    assert oracle.in_simplex(tri, [0.25, 0.25], 0.0)
+    assert oracle.in_simplex(tri, [0.5, 0.5], 0.0)           # on the hypotenuse: closed
+    assert oracle.in_simplex(tri, [0.0, 0.0], 0.0)           # a vertex
+    assert not oracle.in_simplex(tri, [0.5 + 1e-9, 0.5 + 1e-9], 0.0)
+    assert oracle.in_simplex(tri, [0.5 + 5e-8, 0.5 + 5e-8], 1e-7)     # inside the LP's tolerance band
+    assert not oracle.in_simplex(tri, [0.5 + 2e-7, 0.5 + 2e-7], 1e-7)
+    seg = np.array([[0.0, 0.0], [1.0, 1.0], [2.0, 2.0]])       # degenerate: a segment
+    assert oracle.in_simplex(seg, [1.5, 1.5], 1e-7)
+    assert not oracle.in_simplex(seg, [2.5, 2.5], 1e-7)
+    assert not oracle.in_simplex(seg, [1.0, 1.0 + 1e-6], 1e-7)
+    pt = np.array([[1.0, 1.0], [1.0, 1.0], [1.0, 1.0]])        # degenerate: a point
+    assert oracle.in_simplex(pt, [1.0, 1.0], 0.0)
+    assert not oracle.in_simplex(pt, [1.0, 1.1], 1e-7)
