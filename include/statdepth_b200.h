@@ -63,7 +63,19 @@ enum sd_bd_impl {
 
 enum sd_option {
     SD_OPT_BD_IMPL = 1,       /* enum sd_bd_impl */
-    SD_OPT_MBD_FORCE_FALLBACK = 2 /* 1: rank every row with the generic (slow) path; testing aid */
+    SD_OPT_MBD_FORCE_FALLBACK = 2, /* 1: rank every row with the generic (slow) path; testing aid */
+    SD_OPT_PROFILE = 3            /* 1: bracket every kernel phase with CUDA events (sd_get_phase_ns) */
+};
+
+/* phases of the modified-band-depth pipeline reported by sd_get_phase_ns */
+enum sd_phase {
+    SD_PHASE_MBD_SPLITTERS = 0,
+    SD_PHASE_MBD_PARTITION = 1,
+    SD_PHASE_MBD_RANK = 2,
+    SD_PHASE_MBD_GENERIC = 3,
+    SD_PHASE_BD_MASKS = 4,
+    SD_PHASE_BD_PAIRS = 5,
+    SD_PHASE_COUNT = 8
 };
 
 /* nanoseconds of the LAST call on this context, from CUDA events on the context's stream */
@@ -92,6 +104,9 @@ int sd_destroy(sd_ctx *ctx);
 int sd_device_info(sd_ctx *ctx, sd_devinfo *out);
 int sd_set_option(sd_ctx *ctx, int option, int64_t value);
 int sd_get_timings(sd_ctx *ctx, sd_timings *out);
+/* with SD_OPT_PROFILE on: device nanoseconds per phase (enum sd_phase) of the LAST call, summed over
+ * its launches of that phase; out must hold SD_PHASE_COUNT entries. */
+int sd_get_phase_ns(sd_ctx *ctx, int64_t *out);
 /* the context's cudaStream_t (as void*), so a caller can order its own work / events on it */
 void *sd_stream(sd_ctx *ctx);
 

@@ -17,7 +17,8 @@ STATUS_NAMES = {1: "SD_ERR_INVALID", 2: "SD_ERR_CUDA", 3: "SD_ERR_NO_DEVICE", 4:
                 5: "SD_ERR_OVERFLOW", 6: "SD_ERR_UNSUPPORTED"}
 LAYOUT_TN, LAYOUT_NT = 0, 1
 BD_AUTO, BD_BITS, BD_GEMM = 0, 1, 2
-OPT_BD_IMPL, OPT_MBD_FORCE_FALLBACK = 1, 2
+OPT_BD_IMPL, OPT_MBD_FORCE_FALLBACK, OPT_PROFILE = 1, 2, 3
+PHASES = ("mbd_splitters", "mbd_partition", "mbd_rank", "mbd_generic", "bd_masks", "bd_pairs", "p6", "p7")
 
 
 class EngineUnavailable(RuntimeError):
@@ -54,6 +55,7 @@ SIGNATURES = {
     "sd_device_info": (C.c_int, [C.c_void_p, C.POINTER(DevInfo)]),
     "sd_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "sd_get_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
+    "sd_get_phase_ns": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sd_stream": (C.c_void_p, [C.c_void_p]),
     "sd_band_depth_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p,
                                     C.c_int64, C.c_int, C.c_int, C.c_void_p]),
@@ -144,6 +146,12 @@ class Engine:
         self._check(self.lib.sd_get_timings(self._ctx, C.byref(t)))
         return dict(h2d_ns=t.h2d_ns, kernel_ns=t.kernel_ns, d2h_ns=t.d2h_ns, launches=t.launches,
                     fallback_rows=t.fallback_rows)
+
+    def phase_ns(self) -> dict:
+        """Per-phase device time of the last call (needs set_option(OPT_PROFILE, 1))."""
+        out = np.zeros(len(PHASES), dtype=np.int64)
+        self._check(self.lib.sd_get_phase_ns(self._ctx, _ptr(out)))
+        return {k: int(v) for k, v in zip(PHASES, out) if v}
 
     def set_option(self, option: int, value: int):
         self._check(self.lib.sd_set_option(self._ctx, int(option), int(value)))

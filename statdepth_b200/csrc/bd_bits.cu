@@ -215,17 +215,21 @@ int bd_strict_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const 
     for (i64 q0 = 0; q0 < nq; q0 += QB) {
         const int nqb = (int)(nq - q0 < QB ? nq - q0 : QB);
         dim3 mgrid((unsigned)ceil_div(n, 128), (unsigned)W, (unsigned)ceil_div(nqb, MASK_QT));
+        SD_TRY(prof_begin(ctx, SD_PHASE_BD_MASKS));
         bd_mask_kernel<<<mgrid, 128, 0, st>>>(dX, T, n, ld, d_q + q0, nqb, (int)W, M, ctx->d_status);
+        SD_TRY(prof_end(ctx));
         ctx->last.launches++;
+        SD_TRY(prof_begin(ctx, SD_PHASE_BD_PAIRS));
         if (j == 2) {
             dim3 pgrid((unsigned)ceil_div(n, PAIR_TJ), (unsigned)nqb);
             bd_pair_kernel<<<pgrid, PAIR_TJ, 0, st>>>(M, n, (int)W, d_q + q0, d_out + q0);
         } else {
             const i64 npairs = n * (n - 1) / 2;
-            if (npairs == 0) continue;
+            if (npairs == 0) { SD_TRY(prof_end(ctx)); continue; }
             dim3 tgrid((unsigned)ceil_div(npairs, 256), (unsigned)nqb);
             bd_triple_kernel<<<tgrid, 256, 0, st>>>(M, n, (int)W, d_q + q0, d_out + q0);
         }
+        SD_TRY(prof_end(ctx));
         ctx->last.launches++;
         SD_CUDA(cudaGetLastError());
     }

@@ -93,6 +93,12 @@ struct sd_ctx {
     sd_timings last = {0, 0, 0, 0, 0};
     int bd_impl = SD_BD_AUTO;
     int mbd_force_fallback = 0;
+    int profile = 0;
+    static const int MAX_PROF = 256;                 // event pairs per call when profiling
+    cudaEvent_t prof_ev[2 * MAX_PROF] = {};          // created lazily
+    int prof_phase[MAX_PROF] = {};
+    int prof_n = 0;
+    int64_t phase_ns[SD_PHASE_COUNT] = {};
     sd::DevBuf buf[sd::NUM_BUFS];
     int *d_status = nullptr;  // device int[4]: [0] status bits, [1] MBD rows ranked by the generic path
     int *h_status = nullptr;  // pinned mirror
@@ -105,6 +111,9 @@ int begin_call(sd_ctx *ctx);                 // resets status, records ev[0]
 int mark(sd_ctx *ctx, int which);            // records ev[which]
 int end_call(sd_ctx *ctx, bool had_copies);  // syncs, fills ctx->last, maps status bits to errors
 int check_status(sd_ctx *ctx);               // (after sync) translate *h_status
+// profiling brackets (no-ops unless SD_OPT_PROFILE): prof_begin before a phase's launches, prof_end after
+int prof_begin(sd_ctx *ctx, int phase);
+int prof_end(sd_ctx *ctx);
 
 // kernels / drivers implemented in the other translation units (all stream-ordered on ctx->stream)
 int band_depth_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq, int j,

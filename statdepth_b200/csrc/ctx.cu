@@ -44,8 +44,27 @@ void DevBuf::release() {
 int begin_call(sd_ctx *ctx) {
     SD_CUDA(cudaSetDevice(ctx->device));
     ctx->last = sd_timings{0, 0, 0, 0, 0};
+    ctx->prof_n = 0;
+    for (int i = 0; i < SD_PHASE_COUNT; ++i) ctx->phase_ns[i] = 0;
     SD_CUDA(cudaMemsetAsync(ctx->d_status, 0, 4 * sizeof(int), ctx->stream));
     SD_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    return SD_OK;
+}
+
+int prof_begin(sd_ctx *ctx, int phase) {
+    if (!ctx->profile || ctx->prof_n >= sd_ctx::MAX_PROF) return SD_OK;
+    const int i = ctx->prof_n;
+    for (int k = 0; k < 2; ++k)
+        if (!ctx->prof_ev[2 * i + k]) SD_CUDA(cudaEventCreate(&ctx->prof_ev[2 * i + k]));
+    ctx->prof_phase[i] = phase;
+    SD_CUDA(cudaEventRecord(ctx->prof_ev[2 * i], ctx->stream));
+    return SD_OK;
+}
+
+int prof_end(sd_ctx *ctx) {
+    if (!ctx->profile || ctx->prof_n >= sd_ctx::MAX_PROF) return SD_OK;
+    SD_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], ctx->stream));
+    ctx->prof_n++;
     return SD_OK;
 }
 
@@ -81,6 +100,10 @@ int end_call(sd_ctx *ctx, bool had_copies) {
     SD_CUDA(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
     ctx->last.kernel_ns = (int64_t)(ms * 1e6);
     ctx->last.fallback_rows = ctx->h_status[1];
+    for (int i = 0; i < ctx->prof_n; ++i) {
+        SD_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        ctx->phase_ns[ctx->prof_phase[i]] += (int64_t)(ms * 1e6);
+    }
     return check_status(ctx);
 }
 
@@ -208,6 +231,8 @@ int sd_destroy(sd_ctx *ctx) {
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     for (int i = 0; i < 4; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2 * sd_ctx::MAX_PROF; ++i)
+        if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SD_OK;
@@ -246,6 +271,9 @@ int sd_set_option(sd_ctx *ctx, int option, int64_t value) {
         case SD_OPT_MBD_FORCE_FALLBACK:
             ctx->mbd_force_fallback = value ? 1 : 0;
             return SD_OK;
+        case SD_OPT_PROFILE:
+            ctx->profile = value ? 1 : 0;
+            return SD_OK;
         default:
             sd::set_error("sd_set_option: unknown option %d", option);
             return SD_ERR_INVALID;
@@ -258,6 +286,15 @@ int sd_get_timings(sd_ctx *ctx, sd_timings *out) {
         return SD_ERR_INVALID;
     }
     *out = ctx->last;
+    return SD_OK;
+}
+
+int sd_get_phase_ns(sd_ctx *ctx, int64_t *out) {
+    if (!ctx || !out) {
+        sd::set_error("sd_get_phase_ns: NULL argument");
+        return SD_ERR_INVALID;
+    }
+    for (int i = 0; i < SD_PHASE_COUNT; ++i) out[i] = ctx->phase_ns[i];
     return SD_OK;
 }
 

@@ -527,22 +527,30 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         } else {
             SD_CUDA(cudaMemsetAsync(cursor, 0, (size_t)Tc * (P + 1) * sizeof(int), st));
             if (P > 1) {
+                SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SPLITTERS));
                 mbd_splitters_kernel<<<(unsigned)rows, 512, (size_t)S * sizeof(double), st>>>(
                     Xb, n, ld, P, S, splitters, ctx->d_status);
+                SD_TRY(prof_end(ctx));
                 ctx->last.launches++;
             }
             dim3 pgrid((unsigned)ceil_div(n, PART_CHUNK), (unsigned)rows);
+            SD_TRY(prof_begin(ctx, SD_PHASE_MBD_PARTITION));
             mbd_partition_kernel<<<pgrid, 256, 0, st>>>(Xb, n, ld, P, splitters, cursor, rowflag, part_x, part_j,
                                                         row_stride, ctx->d_status);
+            SD_TRY(prof_end(ctx));
             ctx->last.launches++;
             const i64 nwarps = rows * P;
+            SD_TRY(prof_begin(ctx, SD_PHASE_MBD_RANK));
             mbd_rank_kernel<<<(unsigned)ceil_div(nwarps, RANK_WARPS), RANK_WARPS * 32, 0, st>>>(
                 P, nwarps, cursor, rowflag, part_x, part_j, row_stride, r0, o);
+            SD_TRY(prof_end(ctx));
             ctx->last.launches++;
         }
         // rows flagged as overflowing (or all rows when forced): generic path; idle CTAs exit at once
+        SD_TRY(prof_begin(ctx, SD_PHASE_MBD_GENERIC));
         mbd_fallback_kernel<<<(unsigned)rows, 1024, 0, st>>>(Xb, n, ld, NP, rowflag, (u64 *)part_x, row_stride, r0, o,
                                                              ctx->d_status, fb_count);
+        SD_TRY(prof_end(ctx));
         ctx->last.launches++;
         SD_CUDA(cudaGetLastError());
     }

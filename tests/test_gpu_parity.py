@@ -1,0 +1,323 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the CPU oracle and the reference's golden vectors.
+
+Bar (north star): integer counts, ranks and depth orderings bit-exact; float64 depths within 1e-12
+relative.  All inputs are seeded; sizes are chosen so the oracle finishes in seconds; BASELINE's full
+sizes are covered by size-independent properties (additivity over time rows, the closed-form
+checksum of tie-free ranks, depth bounds) plus an oracle comparison on a row slice.
+"""
+from math import comb
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from api_cases import check_case
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12  # float64 proportions / L1 / Oja (north star); counts are compared with ==
+
+
+def walks(seed, T, n):
+    return np.random.default_rng(seed).standard_normal((T, n)).cumsum(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# modified band depth (relax=True)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,n,seed", [(100, 200, 0), (5, 6, 1), (3, 2, 2), (1, 1, 3), (64, 513, 4), (17, 1000, 5),
+                                      (256, 4096, 6), (33, 12345, 7)])
+def test_mbd_counts_bit_exact(engine, oracle, T, n, seed):
+    X = walks(seed, T, n)
+    for j in (2, 3):
+        got = engine.band_depth_counts(X, None, j, True)
+        assert (got == oracle.mbd_counts_all(X, j=j)).all()
+    assert engine.timings()["fallback_rows"] == 0  # well-spread data never needs the generic path
+
+
+@pytest.mark.parametrize("maker", ["round", "few", "constant", "half_constant", "outliers", "sorted", "negzero"])
+def test_mbd_ties_and_skew(engine, oracle, maker):
+    rng = np.random.default_rng(11)
+    T, n = 24, 6000
+    X = rng.standard_normal((T, n)).cumsum(0)
+    if maker == "round":
+        X = np.round(X)
+    elif maker == "few":
+        X = rng.integers(0, 3, size=(T, n)).astype(np.float64)
+    elif maker == "constant":
+        X = np.full((T, n), 2.5)
+    elif maker == "half_constant":
+        X[:, : n // 2] = 1.0
+    elif maker == "outliers":
+        X[:, :5] = 1e300
+        X[:, 5:9] = -1e300
+    elif maker == "sorted":
+        X = np.sort(X, axis=1)
+    elif maker == "negzero":
+        X = np.where(rng.random((T, n)) < 0.5, 0.0, -0.0)
+    got = engine.band_depth_counts(X, None, 2, True)
+    assert (got == oracle.mbd_counts_all(X)).all()
+
+
+def test_mbd_generic_path_forced(engine, oracle):
+    """SD_OPT_MBD_FORCE_FALLBACK: the one-CTA-per-row bitonic path alone must give the same counts."""
+    from statdepth_b200 import _engine as E
+    X = walks(21, 19, 5000)
+    X[:, 100:200] = np.round(X[:, 100:200])
+    try:
+        engine.set_option(E.OPT_MBD_FORCE_FALLBACK, 1)
+        for j in (2, 3):
+            assert (engine.band_depth_counts(X, None, j, True) == oracle.mbd_counts_all(X, j=j)).all()
+        assert engine.timings()["fallback_rows"] == 19
+        Xs = walks(22, 7, 300)
+        assert (engine.band_depth_counts(Xs, None, 2, True) == oracle.mbd_counts_all(Xs)).all()
+    finally:
+        engine.set_option(E.OPT_MBD_FORCE_FALLBACK, 0)
+
+
+def test_ranks_bit_exact(engine, oracle):
+    X = walks(31, 9, 3000)
+    X[:, :50] = np.round(X[:, :50])
+    below, above = engine.band_ranks(X)
+    _, rb, ra = oracle.mbd_counts_all(X, want_ranks=True)
+    assert (below == rb).all() and (above == ra).all()
+
+
+def test_layouts_queries_and_ld(engine, oracle):
+    X = walks(41, 40, 700)
+    ref = oracle.mbd_counts_all(X)
+    q = np.array([5, 699, 0, 5, 333])
+    assert (engine.band_depth_counts(X, q, 2, True) == ref[q]).all()
+    Xf = np.asfortranarray(X)  # what a column-built DataFrame hands over: SD_LAYOUT_NT + device transpose
+    assert (engine.band_depth_counts(Xf, None, 2, True) == ref).all()
+    sref = oracle.bd_counts(X, q)
+    assert (engine.band_depth_counts(Xf, q, 2, False) == sref).all()
+    wide = np.zeros((40, 900))
+    wide[:, :700] = X
+    out = engine.band_depth_counts_ptr(wide.ctypes.data, 40, 700, 900, None, 2, True)
+    assert (out == ref).all()
+
+
+def test_nonfinite_is_rejected(engine):
+    from statdepth_b200 import EngineError
+    X = walks(51, 8, 1200)
+    X[3, 77] = np.nan
+    for relax in (True, False):
+        with pytest.raises(EngineError, match="NONFINITE"):
+            engine.band_depth_counts(X, None, 2, relax)
+    X[3, 77] = np.inf
+    with pytest.raises(EngineError, match="NONFINITE"):
+        engine.band_depth_counts(X, None, 2, True)
+
+
+def test_mbd_full_size_properties(engine, oracle):
+    """BASELINE config 2 (100k curves x 1024 points): additivity over row blocks, the tie-free checksum
+    sum_c count_c = T * (n*C(n-1,2) - 2*C(n,3)), depth <= (n-2)/n, and the oracle on a 48-row slice."""
+    T, n = 1024, 100_000
+    X = walks(1, T, n)
+    full = engine.band_depth_counts(X, None, 2, True)
+    assert engine.timings()["fallback_rows"] == 0
+    assert int(full.sum()) == T * (n * comb(n - 1, 2) - 2 * comb(n, 3))
+    a = engine.band_depth_counts(X[:500], None, 2, True)
+    b = engine.band_depth_counts(X[500:], None, 2, True)
+    assert (a + b == full).all()
+    sl = engine.band_depth_counts(X[500:548], None, 2, True)
+    assert (sl == oracle.mbd_counts_all(X[500:548])).all()
+    depth = full / T / comb(n, 2)
+    assert depth.max() <= (n - 2) / n and depth.min() > 0
+    # tie stress at full width: integers -> heavy ties, parts overflow, generic path takes over
+    Xr = np.round(X[:16])
+    assert (engine.band_depth_counts(Xr, None, 2, True) == oracle.mbd_counts_all(Xr)).all()
+    assert engine.timings()["fallback_rows"] > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# strict band depth (relax=False)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,n,seed", [(100, 200, 0), (5, 6, 1), (2, 3, 2), (31, 300, 3), (32, 257, 4), (33, 256, 5),
+                                      (64, 1000, 6), (97, 777, 7)])
+def test_strict_counts_bit_exact(engine, oracle, T, n, seed):
+    X = walks(seed, T, n)
+    assert (engine.band_depth_counts(X, None, 2, False) == oracle.bd_counts(X)).all()
+
+
+@pytest.mark.parametrize("maker", ["round", "noncrossing", "constant"])
+def test_strict_ties_and_many_survivors(engine, oracle, maker):
+    """Rounded curves tie with the query; non-crossing curves (the reference's own generator) make
+    about half of all pairs survive every word, which exercises the survivor queue drain."""
+    rng = np.random.default_rng(13)
+    T, n = 70, 600
+    if maker == "round":
+        X = np.round(rng.standard_normal((T, n)).cumsum(0))
+    elif maker == "noncrossing":
+        X = np.outer(rng.random(T) + 0.1, rng.random(n))
+    else:
+        X = np.full((T, n), 1.0)
+    assert (engine.band_depth_counts(X, None, 2, False) == oracle.bd_counts(X)).all()
+
+
+def test_strict_j3(engine, oracle):
+    X = walks(61, 40, 60)
+    assert (engine.band_depth_counts(X, None, 3, False) == oracle.bd_counts(X, j=3)).all()
+    Xr = np.round(X)
+    assert (engine.band_depth_counts(Xr, [0, 7, 59], 3, False) == oracle.bd_counts(Xr, [0, 7, 59], j=3)).all()
+
+
+def test_strict_full_size_sample(engine, oracle):
+    """BASELINE config 3 (8192 curves x 512 points): all 8192 queries on the GPU, 48 of them checked
+    against the oracle; plus the bound count <= C(n-1,2)."""
+    T, n = 512, 8192
+    X = walks(2, T, n)
+    got = engine.band_depth_counts(X, None, 2, False)
+    q = np.random.default_rng(0).choice(n, 48, replace=False)
+    assert (got[q] == oracle.bd_counts(X, q)).all()
+    assert got.max() <= comb(n - 1, 2) and got.min() >= 0
+    sub = engine.band_depth_counts(X, q, 2, False)
+    assert (sub == got[q]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# public API against the reference's golden vectors
+# ------------------------------------------------------------------------------------------------
+def test_golden_vectors_through_public_api(golden):
+    from statdepth_b200 import FunctionalDepth, PointcloudDepth
+    n = 0
+    for case in golden.values():
+        if case["kind"] in ("functional", "multivariate", "pointcloud"):
+            check_case(case, FunctionalDepth, PointcloudDepth, rtol=RTOL)
+            n += 1
+    assert n >= 30
+
+
+def test_cfg1_reference_values(golden):
+    """BASELINE config 1: the two curves the reference itself computed (88 s of CPU) -- strict bit-exact."""
+    from statdepth_b200 import FunctionalDepth
+    df = pd.DataFrame(walks(0, 100, 200))
+    s = FunctionalDepth([df], to_compute=[0, 1], relax=False)
+    assert s.values.tolist() == golden["cfg1_200x100_strict"]["depths"]
+    r = FunctionalDepth([df], to_compute=[0, 1], relax=True)
+    np.testing.assert_allclose(r.values, golden["cfg1_200x100_relax"]["depths"], rtol=RTOL)
+
+
+def test_k_sampled_and_batched(engine, oracle, golden):
+    from statdepth_b200 import FunctionalDepth
+    case = golden["walk_K3_seed123"]
+    np.random.seed(case["np_seed"])
+    res = FunctionalDepth([pd.DataFrame(np.array(case["X"]))], K=case["K"], **case["kwargs"])
+    np.testing.assert_allclose(res.values, case["depths"], rtol=RTOL)
+    # batched ABI directly: random sub-populations of one matrix
+    rng = np.random.default_rng(71)
+    X = walks(72, 30, 90)
+    B = 7
+    mem = (rng.random((B, 90)) < 0.6).astype(np.uint8)
+    qs = np.stack([rng.choice(np.flatnonzero(mem[b]), 3, replace=False) for b in range(B)])
+    for relax in (True, False):
+        got = engine.band_depth_counts_batched(X, mem, qs, 2, relax)
+        for b in range(B):
+            cols = np.flatnonzero(mem[b])
+            loc = [int(np.searchsorted(cols, g)) for g in qs[b]]
+            sub = np.ascontiguousarray(X[:, cols])
+            exp = oracle.mbd_counts_all(sub)[loc] if relax else oracle.bd_counts(sub, loc)
+            assert (got[b] == exp).all()
+
+
+def test_reference_test_suite_types():
+    """The reference's own 5 tests (tests/test_statdepth.py:22-73), same calls, same assertions."""
+    from statdepth_b200 import FunctionalDepth, PointcloudDepth
+    from statdepth_b200.testing import (generate_noisy_multivariate, generate_noisy_pointcloud,
+                                        generate_noisy_univariate)
+    df = generate_noisy_univariate()
+    bd = FunctionalDepth([df], containment='r2')
+    for obj in (bd, bd.ordered(), bd.median(), bd.deepest(n=2), bd.outlying(n=2)):
+        assert isinstance(obj, pd.Series)
+    assert isinstance(FunctionalDepth([df], K=5, containment='r2'), pd.Series)
+    for c, npts in (('l1', 10), ('simplex', 10), ('oja', 20)):
+        pc = generate_noisy_pointcloud(n=npts, d=2)
+        r = PointcloudDepth(pc, containment=c)
+        for obj in (r, r.ordered(), r.median(), r.deepest(n=2), r.outlying(n=2)):
+            assert isinstance(obj, pd.Series)
+        assert isinstance(PointcloudDepth(pc, K=2, containment=c), pd.Series)
+    mv = FunctionalDepth(generate_noisy_multivariate(), containment='simplex')
+    assert isinstance(mv, pd.Series) and isinstance(mv.ordered(), pd.Series)
+
+
+# ------------------------------------------------------------------------------------------------
+# point clouds and multivariate simplex depth
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,seed", [(300, 2, 0), (257, 3, 1), (64, 1, 2), (100, 5, 3), (1500, 2, 4)])
+def test_l1_depth(engine, oracle, n, d, seed):
+    P = np.random.default_rng(seed).standard_normal((n, d))
+    got = engine.l1_depth(P)
+    exp = oracle.l1_depth(P)
+    np.testing.assert_allclose(got, exp, rtol=RTOL)
+    assert (got == exp).all()  # same IEEE operations in the same order: identical bits
+    q = [3, 0, n - 1]
+    assert (engine.l1_depth(P, q) == exp[q]).all()
+
+
+def test_l1_duplicates_propagate_nan(engine, oracle):
+    P = np.random.default_rng(5).standard_normal((20, 2))
+    P[7] = P[3]
+    got, exp = engine.l1_depth(P), oracle.l1_depth(P)
+    assert np.isnan(got[[3, 7]]).all() and np.isnan(exp[[3, 7]]).all()  # 0/0, as in the reference
+
+
+@pytest.mark.parametrize("n,d,seed", [(40, 2, 0), (18, 3, 1), (30, 1, 2), (120, 2, 3)])
+def test_simplicial_counts(engine, oracle, n, d, seed):
+    P = np.random.default_rng(seed).standard_normal((n, d))
+    assert (engine.simplicial_counts(P) == oracle.simplicial_counts(P)).all()
+    assert (engine.simplicial_counts(P, [1, 0], 0.0) == oracle.simplicial_counts(P, [1, 0], 0.0)).all()
+
+
+def test_simplicial_degenerate_inputs(engine, oracle):
+    rng = np.random.default_rng(8)
+    P = rng.integers(0, 4, size=(25, 2)).astype(np.float64)  # lattice: collinear triples, duplicates
+    for tol in (0.0, 1e-7):
+        assert (engine.simplicial_counts(P, None, tol) == oracle.simplicial_counts(P, None, tol)).all()
+    L = np.outer(rng.random(12), [1.0, 2.0, -1.0])  # all points on one line in 3-D
+    assert (engine.simplicial_counts(L) == oracle.simplicial_counts(L)).all()
+
+
+@pytest.mark.parametrize("n,d,seed", [(60, 2, 0), (20, 3, 1)])
+def test_oja(engine, oracle, n, d, seed):
+    from scipy.spatial import ConvexHull
+    P = np.random.default_rng(seed).standard_normal((n, d))
+    hv = ConvexHull(P).volume
+    np.testing.assert_allclose(engine.oja(P, hv), oracle.oja(P, hv), rtol=RTOL)
+    pool = np.array([0, 3, 5, 9, 11, 12])
+    np.testing.assert_allclose(engine.oja(P, hv, pool, pool), oracle.oja(P, hv, pool, pool), rtol=RTOL)
+
+
+@pytest.mark.parametrize("N,T,d,seed", [(12, 9, 2, 0), (9, 5, 3, 1), (10, 7, 1, 2), (30, 16, 2, 3)])
+def test_simplex_depth_counts(engine, oracle, N, T, d, seed):
+    F = np.random.default_rng(seed).standard_normal((N, T, d)).cumsum(1)
+    for relax in (False, True):
+        assert (engine.simplex_depth_counts(F, None, relax) == oracle.simplex_depth_counts(F, None, relax)).all()
+    assert (engine.simplex_depth_counts(F, [2, 0], True, 0.0) == oracle.simplex_depth_counts(F, [2, 0], True, 0.0)).all()
+
+
+def test_simplex_depth_reference_fixture(engine, oracle):
+    """The reference's multivariate generator makes 100% degenerate simplices (all curves are scalar
+    multiples of one base curve): containment reduces to 'r between min r_i and max r_i'."""
+    from statdepth_b200.testing import generate_noisy_multivariate
+    for seed, d in ((0, 3), (1, 3), (5, 2)):
+        data = generate_noisy_multivariate(num_curves=7, n=6, d=d, seed=seed)
+        F = np.stack([x.values for x in data])
+        for relax in (False, True):
+            assert (engine.simplex_depth_counts(F, None, relax) == oracle.simplex_depth_counts(F, None, relax)).all()
+
+
+def test_homogeneity_and_permutation_test(golden):
+    from statdepth_b200.homogeneity import FunctionalHomogeneity, permutation_test
+    for m in ("p1", "p2", "p3"):
+        case = golden["functional_%s" % m]
+        F = pd.DataFrame(np.array(case["F"]), columns=["F%d" % i for i in range(7)])
+        G = pd.DataFrame(np.array(case["G"]), columns=["G%d" % i for i in range(6)])
+        h = FunctionalHomogeneity([F], [G], method=m, quiet=True).homogeneity()
+        np.testing.assert_allclose(float(np.asarray(h).ravel()[0]), case["value"], rtol=RTOL)
+    rng = np.random.default_rng(5)
+    F = pd.DataFrame(rng.standard_normal((32, 24)).cumsum(0))
+    G = pd.DataFrame(rng.standard_normal((32, 24)).cumsum(0) + 6.0)
+    out = permutation_test(F, G, method='p1', B=20, seed=5)
+    assert out["null"].shape == (20,) and 0.0 < out["p_value"] <= 1.0
+    assert out["p_value"] < 0.2  # a 6-sigma shift is not exchangeable
