@@ -110,22 +110,40 @@ __global__ void __launch_bounds__(256) mbd_partition_kernel(const double *__rest
     u32 *pj = part_j + (i64)row * row_stride;
     int *cur = cursor + (i64)row * P;
     bool bad = false, over = false;
-    for (i64 c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
-        const double x = xr[c];
-        bad |= !isfinite(x);
-        // part = number of splitters <= x  (upper bound), branch-free
-        int lo = 0;
-        for (int step = top >> 1; step > 0; step >>= 1) {
-            const int probe = lo + step;
-            if (probe <= nspl && spl[probe - 1] <= x) lo = probe;
+    constexpr int ILP = 4;  // independent load -> search -> atomic -> store chains per thread
+    for (i64 cb = c0 + threadIdx.x; cb < c1; cb += (i64)ILP * blockDim.x) {
+        double x[ILP];
+        int lo[ILP], slot[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const i64 c = cb + (i64)u * blockDim.x;
+            x[u] = c < c1 ? xr[c] : 0.0;
+            bad |= !isfinite(x[u]);
+            lo[u] = 0;
         }
-        const int slot = atomicAdd(&cur[lo], 1);
-        if (slot < CAP) {
-            const i64 at = (i64)lo * CAP + slot;
-            px[at] = x;
-            pj[at] = (u32)c;
-        } else {
-            over = true;
+        // part = number of splitters <= x  (upper bound), branch-free, the ILP searches interleaved
+        for (int step = top >> 1; step > 0; step >>= 1) {
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) {
+                const int probe = lo[u] + step;
+                if (probe <= nspl && spl[probe - 1] <= x[u]) lo[u] = probe;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const i64 c = cb + (i64)u * blockDim.x;
+            slot[u] = c < c1 ? atomicAdd(&cur[lo[u]], 1) : CAP;
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const i64 c = cb + (i64)u * blockDim.x;
+            if (slot[u] < CAP) {
+                const i64 at = (i64)lo[u] * CAP + slot[u];
+                px[at] = x[u];
+                pj[at] = (u32)c;
+            } else if (c < c1) {
+                over = true;
+            }
         }
     }
     if (bad) atomicOr(status, ST_NONFINITE);
@@ -141,42 +159,55 @@ __device__ __forceinline__ void ce_u32(u32 &a, u32 &b) {
     b = hi;
 }
 
-// sorts 32*EPL keys held as v[i] at element index e = lane*EPL + i, ascending in e
+// Sorts 32*EPL keys held as v[i] at element index e = lane*EPL + i, ascending in e.
+// Bitonic network in its "always ascending" form: the first stage of every merge pairs e with its
+// mirror e ^ (k-1), the remaining stages pair e with e ^ j, and every compare-exchange puts the
+// minimum at the lower index.  Merges that stay inside a lane (k <= EPL) are unrolled on registers;
+// merges across lanes run as ROLLED loops over the lane mask -- the fully unrolled network was
+// ~35k SASS instructions and the kernel spent 70% of its stall samples in stall_no_inst
+// (profiles/ncu_mbd_r01a_summary.md), so code size matters more than loop overhead here.
 template <int EPL>
 __device__ __forceinline__ void warp_bitonic_sort(u32 (&v)[EPL], const int lane) {
-    constexpr int N = 32 * EPL;
+    // 1. every lane sorts its own EPL keys
 #pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
-        if (k <= EPL) {
+    for (int k = 2; k <= EPL; k <<= 1) {
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) {
-                const int p = i ^ (k - 1);
-                if (i < p) ce_u32(v[i], v[p]);
-            }
-        } else {
-            const int lm = k / EPL - 1;
-            const bool lower = (lane & ((k / EPL) >> 1)) == 0;
-            u32 o[EPL];
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) o[i] = __shfl_xor_sync(0xffffffffu, v[EPL - 1 - i], lm);
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) v[i] = lower ? min(v[i], o[i]) : max(v[i], o[i]);
+        for (int i = 0; i < EPL; ++i) {
+            const int p = i ^ (k - 1);
+            if (i < p) ce_u32(v[i], v[p]);
         }
 #pragma unroll
         for (int j = k >> 2; j > 0; j >>= 1) {
-            if (j < EPL) {
 #pragma unroll
-                for (int i = 0; i < EPL; ++i)
-                    if ((i & j) == 0) ce_u32(v[i], v[i | j]);
-            } else {
-                const int lm = j / EPL;
-                const bool lower = (lane & lm) == 0;
+            for (int i = 0; i < EPL; ++i)
+                if ((i & j) == 0) ce_u32(v[i], v[i | j]);
+        }
+    }
+    // 2. merges across kl = 2, 4, .., 32 lanes
+#pragma unroll 1
+    for (int kl = 2; kl <= 32; kl <<= 1) {
+        {   // mirror stage: partner lane = lane ^ (kl-1), partner register = EPL-1-i
+            const bool lower = (lane & (kl >> 1)) == 0;
+            u32 o[EPL];
 #pragma unroll
-                for (int i = 0; i < EPL; ++i) {
-                    const u32 o = __shfl_xor_sync(0xffffffffu, v[i], lm);
-                    v[i] = lower ? min(v[i], o) : max(v[i], o);
-                }
+            for (int i = 0; i < EPL; ++i) o[i] = __shfl_xor_sync(0xffffffffu, v[EPL - 1 - i], kl - 1);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) v[i] = lower ? min(v[i], o[i]) : max(v[i], o[i]);
+        }
+#pragma unroll 1
+        for (int jl = kl >> 2; jl > 0; jl >>= 1) {  // lane-crossing xor stages
+            const bool lower = (lane & jl) == 0;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                const u32 o = __shfl_xor_sync(0xffffffffu, v[i], jl);
+                v[i] = lower ? min(v[i], o) : max(v[i], o);
             }
+        }
+#pragma unroll
+        for (int j = EPL >> 1; j > 0; j >>= 1) {    // in-lane tail of the merge
+#pragma unroll
+            for (int i = 0; i < EPL; ++i)
+                if ((i & j) == 0) ce_u32(v[i], v[i | j]);
         }
     }
 }
@@ -228,11 +259,8 @@ __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u
     hi = warp_max(hi);
     if (lo == hi) {  // every element ties: b = everything in lower parts, a = everything in higher parts
         const i64 b = base, a = o.n - base - cnt;
-#pragma unroll
-        for (int k = 0; k < EPL; ++k) {
-            const int s = lane + 32 * k;
-            if (s < cnt) emit_rank(o, row_global, pj[s], b, a);
-        }
+#pragma unroll 1
+        for (int s = lane; s < cnt; s += 32) emit_rank(o, row_global, pj[s], b, a);
         return;
     }
     // pass 2: monotone 22-bit key | slot id.  x >= lo exactly, every step below is monotone in x.
@@ -255,47 +283,46 @@ __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u
 #pragma unroll
     for (int i = 0; i < EPL; ++i) skeys[i * 32 + lane] = v[i];
     __syncwarp();
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
+#pragma unroll 1
+    for (int i = 0; i < EPL; ++i) {  // rolled on purpose (code size); keys are re-read from shared memory
         const int pos = lane * EPL + i;
         if (pos < cnt) {
-            const u32 key = v[i];
+            const u32 key = skeys[i * 32 + lane];
             const u32 r = key >> 10;
             const int slot = (int)(key & 1023u);
             int rs = pos, re = pos + 1, less = 0, greater = 0;
-            double xs = 0.0;
-            bool have = false;
-            for (int m = pos - 1; m >= 0; --m) {  // equal-key run to the left (normally empty)
-                const u32 km = skeys[(m % EPL) * 32 + m / EPL];
-                if ((km >> 10) != r) break;
-                if (!have) { xs = px[slot]; have = true; }
-                const double xm = px[km & 1023u];
-                less += xm < xs;
-                greater += xm > xs;
-                rs = m;
-            }
-            for (int m = pos + 1; m < cnt; ++m) {  // ... and to the right
-                const u32 km = skeys[(m % EPL) * 32 + m / EPL];
-                if ((km >> 10) != r) break;
-                if (!have) { xs = px[slot]; have = true; }
-                const double xm = px[km & 1023u];
-                less += xm < xs;
-                greater += xm > xs;
-                re = m + 1;
+            // neighbours with the same reduced key (normally none): exact fp64 compares decide
+            const bool left = pos > 0 && (skeys[((pos - 1) % EPL) * 32 + (pos - 1) / EPL] >> 10) == r;
+            const bool right = pos + 1 < cnt && (skeys[((pos + 1) % EPL) * 32 + (pos + 1) / EPL] >> 10) == r;
+            if (left || right) {
+                const double xs = px[slot];
+                for (int m = pos - 1; m >= 0; --m) {
+                    const u32 km = skeys[(m % EPL) * 32 + m / EPL];
+                    if ((km >> 10) != r) break;
+                    const double xm = px[km & 1023u];
+                    less += xm < xs;
+                    greater += xm > xs;
+                    rs = m;
+                }
+                for (int m = pos + 1; m < cnt; ++m) {
+                    const u32 km = skeys[(m % EPL) * 32 + m / EPL];
+                    if ((km >> 10) != r) break;
+                    const double xm = px[km & 1023u];
+                    less += xm < xs;
+                    greater += xm > xs;
+                    re = m + 1;
+                }
             }
             sres[slot] = (u32)(rs + less) | ((u32)(re - greater) << 16);
         }
     }
     __syncwarp();
-#pragma unroll
-    for (int k = 0; k < EPL; ++k) {
-        const int s = lane + 32 * k;
-        if (s < cnt) {
-            const u32 res = sres[s];
-            const i64 b = base + (i64)(res & 0xffffu);
-            const i64 a = o.n - base - (i64)(res >> 16);
-            emit_rank(o, row_global, pj[s], b, a);
-        }
+#pragma unroll 1
+    for (int s = lane; s < cnt; s += 32) {
+        const u32 res = sres[s];
+        const i64 b = base + (i64)(res & 0xffffu);
+        const i64 a = o.n - base - (i64)(res >> 16);
+        emit_rank(o, row_global, pj[s], b, a);
     }
     __syncwarp();
 }
@@ -326,8 +353,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) mbd_rank_kernel(const int P, 
     for (int s = 16; s > 0; s >>= 1) base += __shfl_xor_sync(0xffffffffu, base, s);
     const double *px = part_x + row * row_stride + (i64)part * CAP;
     const u32 *pj = part_j + row * row_stride + (i64)part * CAP;
-    if (cnt <= 128) rank_part<4>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
-    else if (cnt <= 256) rank_part<8>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
+    if (cnt <= 256) rank_part<8>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
     else if (cnt <= 512) rank_part<16>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
     else rank_part<32>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
 }
