@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--T", type=int, default=None)
     ap.add_argument("--cpu-sample-rows", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bd-impl", default="auto", choices=["auto", "bits", "gemm"])
+    ap.add_argument("--nq", type=int, default=None, help="bd workload: number of query curves (default all)")
     return ap.parse_args()
 
 
@@ -176,6 +178,7 @@ def main():
     relax = args.workload == "mbd"
     eng = E.Engine(local)
     eng.set_option(E.OPT_PROFILE, 1)
+    eng.set_option(E.OPT_BD_IMPL, {"auto": E.BD_AUTO, "bits": E.BD_BITS, "gemm": E.BD_GEMM}[args.bd_impl])
     dev = torch.device("cuda", local)
 
     # ---- synthetic input: float64 random walks (they cross), identical on every rank ---------------
@@ -192,7 +195,7 @@ def main():
         nq_local = n
         q_dev = None
     else:       # queries sharded, counts all-gathered
-        lo, hi = sdist.block(n, rank, world)
+        lo, hi = sdist.block(args.nq or n, rank, world)
         Xl = X
         nq_local = hi - lo
         q_dev = torch.arange(lo, hi, dtype=torch.int64, device=dev)
@@ -285,8 +288,9 @@ def main():
             dist.destroy_process_group()
         return
 
-    value = n * args.steps / (ms / 1e3)
-    e2e_value = n * args.steps / (ms_e2e / 1e3)
+    evals = n if relax else (args.nq or n)  # depth evaluations per step
+    value = evals * args.steps / (ms / 1e3)
+    e2e_value = evals * args.steps / (ms_e2e / 1e3)
     peak, peak_src = peaks()
     # roofline of the rank pipeline (all kernels of a step): algorithmic bytes = 8*n*T_local read once + 8*n written
     alg_bytes = 8.0 * n * Tl + 8.0 * n
@@ -313,6 +317,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "curves": n, "time_points": T, "J": 2, "relax": relax,
+                   "queries": evals, "bd_impl": args.bd_impl,
                    "sharding": ("time rows over ranks + int64 all-reduce" if relax else
                                 "query curves over ranks + all-gather") if world > 1 else "single GPU",
                    "l2": "flushed between steps (256 MiB write)" if flush is not None else

@@ -156,6 +156,27 @@ def test_strict_ties_and_many_survivors(engine, oracle, maker):
     assert (engine.band_depth_counts(X, None, 2, False) == oracle.bd_counts(X)).all()
 
 
+@pytest.mark.parametrize("T,n,seed,maker", [(64, 128, 0, "walk"), (100, 200, 1, "walk"), (5, 6, 2, "walk"),
+                                            (130, 300, 3, "round"), (512, 1000, 4, "walk"), (70, 600, 5, "noncrossing"),
+                                            (200, 129, 6, "walk")])
+def test_strict_tcgen05_gram_bit_exact(engine, oracle, T, n, seed, maker):
+    """SD_BD_GEMM: the int8 violation Gram on tcgen05 / TMEM gives the same counts as the oracle."""
+    from statdepth_b200 import _engine as E
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((T, n)).cumsum(0)
+    if maker == "round":
+        X = np.round(X)
+    elif maker == "noncrossing":
+        X = np.outer(rng.random(T) + 0.1, rng.random(n))
+    try:
+        engine.set_option(E.OPT_BD_IMPL, E.BD_GEMM)
+        assert (engine.band_depth_counts(X, None, 2, False) == oracle.bd_counts(X)).all()
+        q = [n - 1, 0, n // 2]
+        assert (engine.band_depth_counts(X, q, 2, False) == oracle.bd_counts(X, q)).all()
+    finally:
+        engine.set_option(E.OPT_BD_IMPL, E.BD_AUTO)
+
+
 def test_strict_j3(engine, oracle):
     X = walks(61, 40, 60)
     assert (engine.band_depth_counts(X, None, 3, False) == oracle.bd_counts(X, j=3)).all()
