@@ -42,49 +42,152 @@ __device__ __forceinline__ i64 comb3_dev(i64 m) {
     return m < 3 ? 0 : (m * (m - 1) / 2) * (m - 2) / 3;
 }
 
-// ---------------------------------------------------------------------------------------------
-// 1. splitters
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) mbd_splitters_kernel(const double *__restrict__ X, i64 n, i64 ld,
-                                                            int P, int S, double *__restrict__ splitters,
-                                                            int *__restrict__ status) {
-    extern __shared__ double smp[];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const double *xr = X + (i64)blockIdx.x * ld;
-    bool bad = false;
-    // strided sample taken in quads of 4 consecutive values (one 32 B sector each)
-    const i64 nquad = n >> 2;
-    const int squad = S >> 2;
-    for (int i = tid; i < S; i += nt) {
-        const i64 idx = (nquad >= squad && squad > 0) ? (((i64)(i >> 2) * nquad) / squad) * 4 + (i & 3)
-                                                       : ((i64)i * n) / S;
-        const double v = xr[idx];
-        bad |= !isfinite(v);
-        smp[i] = v;
+__device__ __forceinline__ void ce_u32(u32 &a, u32 &b) {
+    const u32 lo = min(a, b), hi = max(a, b);
+    a = lo;
+    b = hi;
+}
+
+// Register-resident bitonic network over 32*EPL keys held as v[i] at element index e = lane*EPL + i,
+// in its "always ascending" form: the first stage of every merge pairs e with its mirror e ^ (k-1), the
+// remaining stages pair e with e ^ j, and every compare-exchange puts the minimum at the lower index.
+// Stages inside a lane are unrolled on registers; stages across lanes are ROLLED loops over the lane
+// mask -- the fully unrolled network was ~35k SASS instructions and the rank kernel spent 70% of its
+// stall samples in stall_no_inst (profiles/ncu_mbd_r01a_summary.md): code size matters more than loop
+// overhead here.
+template <int EPL>
+__device__ __forceinline__ void lane_tail(u32 (&v)[EPL]) {  // xor stages j = EPL/2 .. 1
+#pragma unroll
+    for (int j = EPL >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i)
+            if ((i & j) == 0) ce_u32(v[i], v[i | j]);
     }
-    if (bad) atomicOr(status, ST_NONFINITE);
-    __syncthreads();
-    // bitonic sort, "always ascending" form: first stage of each merge mirrors (e ^ (k-1)), the rest e ^ j
-    for (int k = 2; k <= S; k <<= 1) {
-        const int hk = k >> 1;
-        for (int i = tid; i < (S >> 1); i += nt) {
-            const int blk = i / hk, off = i - blk * hk;
-            const int a = blk * k + off, b = blk * k + k - 1 - off;
-            const double va = smp[a], vb = smp[b];
-            if (va > vb) { smp[a] = vb; smp[b] = va; }
+}
+
+template <int EPL>
+__device__ __forceinline__ void lane_sort(u32 (&v)[EPL]) {  // every lane sorts its own EPL keys
+#pragma unroll
+    for (int k = 2; k <= EPL; k <<= 1) {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            const int p = i ^ (k - 1);
+            if (i < p) ce_u32(v[i], v[p]);
         }
-        __syncthreads();
+#pragma unroll
         for (int j = k >> 2; j > 0; j >>= 1) {
-            for (int i = tid; i < (S >> 1); i += nt) {
-                const int a = 2 * j * (i / j) + (i % j), b = a + j;
-                const double va = smp[a], vb = smp[b];
-                if (va > vb) { smp[a] = vb; smp[b] = va; }
+#pragma unroll
+            for (int i = 0; i < EPL; ++i)
+                if ((i & j) == 0) ce_u32(v[i], v[i | j]);
+        }
+    }
+}
+
+// xor stages with lane masks jl_first, jl_first/2, .., 1 followed by the in-lane tail
+template <int EPL>
+__device__ __forceinline__ void warp_merge_tail(u32 (&v)[EPL], const int lane, const int jl_first) {
+#pragma unroll 1
+    for (int jl = jl_first; jl > 0; jl >>= 1) {
+        const bool lower = (lane & jl) == 0;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            const u32 o = __shfl_xor_sync(0xffffffffu, v[i], jl);
+            v[i] = lower ? min(v[i], o) : max(v[i], o);
+        }
+    }
+    lane_tail<EPL>(v);
+}
+
+template <int EPL>
+__device__ __forceinline__ void warp_bitonic_sort(u32 (&v)[EPL], const int lane) {
+    lane_sort<EPL>(v);
+#pragma unroll 1
+    for (int kl = 2; kl <= 32; kl <<= 1) {  // merges across kl lanes
+        {   // mirror stage: partner lane = lane ^ (kl-1), partner register = EPL-1-i
+            const bool lower = (lane & (kl >> 1)) == 0;
+            u32 o[EPL];
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) o[i] = __shfl_xor_sync(0xffffffffu, v[EPL - 1 - i], kl - 1);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) v[i] = lower ? min(v[i], o[i]) : max(v[i], o[i]);
+        }
+        warp_merge_tail<EPL>(v, lane, kl >> 2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. splitters: one CTA per row sorts a strided sample of S = 1024*W values (W = 1, 2, 4 or 8 warps)
+//    as order-preserving u32 images of float(x - x[0]) -- splitters need not be data values, any
+//    non-decreasing sequence works, and 32-bit keys sort on registers at 2 instructions per
+//    compare-exchange.  Each warp sorts 1024 keys (EPL = 32); the 1..3 remaining merge levels exchange
+//    partners through XOR-swizzled shared memory and finish on registers.  v1 (fp64 bitonic in shared
+//    memory, 91 block-wide stages) took 0.56 ms of a 3.6 ms step.
+// ---------------------------------------------------------------------------------------------
+constexpr int SP_THREADS = 256;
+
+__device__ __forceinline__ u32 f32_sortable(float f) {
+    const u32 b = __float_as_uint(f);
+    return b ^ ((b & 0x80000000u) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float f32_unsortable(u32 k) {
+    return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+}
+__device__ __forceinline__ int sp_swz(int g) { return g ^ ((g >> 5) & 31); }
+
+__global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double *__restrict__ X, i64 n, i64 ld,
+                                                                   int P, int S, double *__restrict__ splitters,
+                                                                   int *__restrict__ status) {
+    __shared__ u32 skey[MAX_SAMPLE];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int W = S >> 10;  // warps that hold samples
+    const double *xr = X + (i64)blockIdx.x * ld;
+    const double x0 = xr[0];
+    u32 v[32];
+    if (wid < W) {
+        bool bad = false;
+        // strided sample taken in quads of 4 consecutive values (one 32 B sector each)
+        const i64 nquad = n >> 2;
+        const int squad = S >> 2;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int g = wid * 1024 + lane * 32 + i;
+            const i64 idx = (((i64)(g >> 2) * nquad) / squad) * 4 + (g & 3);
+            const double x = xr[idx];
+            bad |= !isfinite(x);
+            v[i] = f32_sortable(__double2float_rn(x - x0));
+        }
+        if (bad) atomicOr(status, ST_NONFINITE);
+        warp_bitonic_sort<32>(v, lane);
+    }
+    for (int k = 2048; k <= S; k <<= 1) {  // merge levels wider than one warp
+        for (int j = k; j >= 2048; j >>= 1) {  // j == k: mirror stage (g ^ (k-1)); else xor stage (g ^ j/2)
+            __syncthreads();
+            if (wid < W) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) skey[sp_swz(wid * 1024 + lane * 32 + i)] = v[i];
             }
             __syncthreads();
+            if (wid < W) {
+                const int xorv = (j == k) ? (k - 1) : (j >> 1);
+                const bool lower = ((wid * 1024) & (j == k ? (k >> 1) : (j >> 1))) == 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const u32 o = skey[sp_swz((wid * 1024 + lane * 32 + i) ^ xorv)];
+                    v[i] = lower ? min(v[i], o) : max(v[i], o);
+                }
+            }
         }
+        if (wid < W) warp_merge_tail<32>(v, lane, 16);  // strides 512 .. 1 stay inside the warp
     }
+    __syncthreads();
+    if (wid < W) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) skey[sp_swz(wid * 1024 + lane * 32 + i)] = v[i];
+    }
+    __syncthreads();
     double *out = splitters + (i64)blockIdx.x * (P - 1);
-    for (int p = tid + 1; p < P; p += nt) out[p - 1] = smp[((i64)p * S) / P];
+    for (int p = tid + 1; p < P; p += SP_THREADS)
+        out[p - 1] = x0 + (double)f32_unsortable(skey[sp_swz((int)(((i64)p * S) / P))]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -222,65 +325,6 @@ __global__ void __launch_bounds__(PT_THREADS) mbd_partition_kernel(const double 
 // ---------------------------------------------------------------------------------------------
 // 3. per-part warp ranking
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ce_u32(u32 &a, u32 &b) {
-    const u32 lo = min(a, b), hi = max(a, b);
-    a = lo;
-    b = hi;
-}
-
-// Sorts 32*EPL keys held as v[i] at element index e = lane*EPL + i, ascending in e.
-// Bitonic network in its "always ascending" form: the first stage of every merge pairs e with its
-// mirror e ^ (k-1), the remaining stages pair e with e ^ j, and every compare-exchange puts the
-// minimum at the lower index.  Merges that stay inside a lane (k <= EPL) are unrolled on registers;
-// merges across lanes run as ROLLED loops over the lane mask -- the fully unrolled network was
-// ~35k SASS instructions and the kernel spent 70% of its stall samples in stall_no_inst
-// (profiles/ncu_mbd_r01a_summary.md), so code size matters more than loop overhead here.
-template <int EPL>
-__device__ __forceinline__ void warp_bitonic_sort(u32 (&v)[EPL], const int lane) {
-    // 1. every lane sorts its own EPL keys
-#pragma unroll
-    for (int k = 2; k <= EPL; k <<= 1) {
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-            const int p = i ^ (k - 1);
-            if (i < p) ce_u32(v[i], v[p]);
-        }
-#pragma unroll
-        for (int j = k >> 2; j > 0; j >>= 1) {
-#pragma unroll
-            for (int i = 0; i < EPL; ++i)
-                if ((i & j) == 0) ce_u32(v[i], v[i | j]);
-        }
-    }
-    // 2. merges across kl = 2, 4, .., 32 lanes
-#pragma unroll 1
-    for (int kl = 2; kl <= 32; kl <<= 1) {
-        {   // mirror stage: partner lane = lane ^ (kl-1), partner register = EPL-1-i
-            const bool lower = (lane & (kl >> 1)) == 0;
-            u32 o[EPL];
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) o[i] = __shfl_xor_sync(0xffffffffu, v[EPL - 1 - i], kl - 1);
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) v[i] = lower ? min(v[i], o[i]) : max(v[i], o[i]);
-        }
-#pragma unroll 1
-        for (int jl = kl >> 2; jl > 0; jl >>= 1) {  // lane-crossing xor stages
-            const bool lower = (lane & jl) == 0;
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) {
-                const u32 o = __shfl_xor_sync(0xffffffffu, v[i], jl);
-                v[i] = lower ? min(v[i], o) : max(v[i], o);
-            }
-        }
-#pragma unroll
-        for (int j = EPL >> 1; j > 0; j >>= 1) {    // in-lane tail of the merge
-#pragma unroll
-            for (int i = 0; i < EPL; ++i)
-                if ((i & j) == 0) ce_u32(v[i], v[i | j]);
-        }
-    }
-}
-
 __device__ __forceinline__ double warp_min(double v) {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, s));
@@ -299,40 +343,44 @@ struct RankOut {
     i64 full2, full3;      // C(n-1,2), C(n-1,3)
 };
 
-__device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, u32 c, i64 b, i64 a) {
-    atomicAdd((u64 *)&o.acc2[c], (u64)(o.full2 - comb2_dev(b) - comb2_dev(a)));
-    if (o.acc3) atomicAdd((u64 *)&o.acc3[c], (u64)(o.full3 - comb3_dev(b) - comb3_dev(a)));
+// b, a < 2^31: C(m,2) with one 32x32->64 multiply
+__device__ __forceinline__ u64 comb2_u32(u32 m) { return ((u64)m * (u64)(m - 1u)) >> 1; }  // m = 0 -> 0 * (2^32-1) >> 1 = 0
+
+__device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, u32 c, u32 b, u32 a) {
+    atomicAdd((u64 *)&o.acc2[c], (u64)o.full2 - comb2_u32(b) - comb2_u32(a));
+    if (o.acc3) atomicAdd((u64 *)&o.acc3[c], (u64)(o.full3 - comb3_dev((i64)b) - comb3_dev((i64)a)));
     if (o.rank_b) {
         o.rank_b[row_global * o.n + c] = (int)b;
         o.rank_a[row_global * o.n + c] = (int)a;
     }
 }
 
-// skeys / sres: this warp's shared scratch (CAP words each)
+// skeys / sres: this warp's shared scratch (CAP words each).
+// [lo, hi): value range of the part when it is known from the splitters (interior parts); otherwise
+// (first / last part, single-part rows) have_range is false and the range is measured.
 template <int EPL>
 __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u32 *__restrict__ pj, const int cnt,
-                                          const i64 base, const i64 row_global, const RankOut &o, u32 *skeys,
-                                          u32 *sres, const int lane) {
-    // pass 1: range of the part
-    double lo = INFINITY, hi = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < EPL; ++k) {
-        const int s = lane + 32 * k;
-        if (s < cnt) {
+                                          const u32 base, const i64 row_global, const RankOut &o, u32 *skeys,
+                                          u32 *sres, const int lane, double lo, double hi, const bool have_range) {
+    const u32 n32 = (u32)o.n;
+    if (!have_range) {
+        lo = INFINITY;
+        hi = -INFINITY;
+#pragma unroll 1
+        for (int s = lane; s < cnt; s += 32) {
             const double x = px[s];
             lo = fmin(lo, x);
             hi = fmax(hi, x);
         }
-    }
-    lo = warp_min(lo);
-    hi = warp_max(hi);
-    if (lo == hi) {  // every element ties: b = everything in lower parts, a = everything in higher parts
-        const i64 b = base, a = o.n - base - cnt;
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (lo == hi) {  // every element ties: b = everything in lower parts, a = everything in higher parts
 #pragma unroll 1
-        for (int s = lane; s < cnt; s += 32) emit_rank(o, row_global, pj[s], b, a);
-        return;
+            for (int s = lane; s < cnt; s += 32) emit_rank(o, row_global, pj[s], base, n32 - base - (u32)cnt);
+            return;
+        }
     }
-    // pass 2: monotone 22-bit key | slot id.  x >= lo exactly, every step below is monotone in x.
+    // monotone 22-bit key | slot id.  lo <= x (exactly), every step below is monotone in x.
     const double scale = (double)KEY_MAX / (hi - lo);
     u32 v[EPL];
 #pragma unroll
@@ -348,39 +396,56 @@ __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u
         v[k] = key;
     }
     warp_bitonic_sort<EPL>(v, lane);
-    // sorted position pos = lane*EPL + i lives at skeys[i*32 + lane] (conflict-free)
+
+    // equal-key neighbours (collisions of distinct values or true ties) are rare: detect them on registers
+    const u32 prev_lane = __shfl_up_sync(0xffffffffu, v[EPL - 1], 1);
+    const u32 next_lane = __shfl_down_sync(0xffffffffu, v[0], 1);
+    bool any_run = false;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) skeys[i * 32 + lane] = v[i];
-    __syncwarp();
-#pragma unroll 1
-    for (int i = 0; i < EPL; ++i) {  // rolled on purpose (code size); keys are re-read from shared memory
+    for (int i = 0; i < EPL; ++i) {
         const int pos = lane * EPL + i;
-        if (pos < cnt) {
+        const u32 r = v[i] >> 10;
+        const u32 kl = i > 0 ? v[i - 1] : prev_lane;
+        const u32 kr = i + 1 < EPL ? v[i + 1] : next_lane;
+        const bool left = pos > 0 && (kl >> 10) == r;
+        const bool right = pos + 1 < cnt && (kr >> 10) == r;
+        const bool in_run = pos < cnt && (left || right);
+        any_run |= in_run;
+        if (pos < cnt && !in_run) sres[v[i] & 1023u] = (u32)pos | ((u32)(pos + 1) << 16);
+    }
+    if (__any_sync(0xffffffffu, any_run)) {
+        // slow path: publish the sorted keys (pos = lane*EPL + i at skeys[i*32 + lane]) and let every
+        // element of a run count, with exact fp64 compares, its run mates below / above it
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) skeys[i * 32 + lane] = v[i];
+        __syncwarp();
+#pragma unroll 1
+        for (int i = 0; i < EPL; ++i) {
+            const int pos = lane * EPL + i;
+            if (pos >= cnt) break;
             const u32 key = skeys[i * 32 + lane];
             const u32 r = key >> 10;
-            const int slot = (int)(key & 1023u);
-            int rs = pos, re = pos + 1, less = 0, greater = 0;
-            // neighbours with the same reduced key (normally none): exact fp64 compares decide
             const bool left = pos > 0 && (skeys[((pos - 1) % EPL) * 32 + (pos - 1) / EPL] >> 10) == r;
             const bool right = pos + 1 < cnt && (skeys[((pos + 1) % EPL) * 32 + (pos + 1) / EPL] >> 10) == r;
-            if (left || right) {
-                const double xs = px[slot];
-                for (int m = pos - 1; m >= 0; --m) {
-                    const u32 km = skeys[(m % EPL) * 32 + m / EPL];
-                    if ((km >> 10) != r) break;
-                    const double xm = px[km & 1023u];
-                    less += xm < xs;
-                    greater += xm > xs;
-                    rs = m;
-                }
-                for (int m = pos + 1; m < cnt; ++m) {
-                    const u32 km = skeys[(m % EPL) * 32 + m / EPL];
-                    if ((km >> 10) != r) break;
-                    const double xm = px[km & 1023u];
-                    less += xm < xs;
-                    greater += xm > xs;
-                    re = m + 1;
-                }
+            if (!(left || right)) continue;
+            const int slot = (int)(key & 1023u);
+            const double xs = px[slot];
+            int rs = pos, re = pos + 1, less = 0, greater = 0;
+            for (int m = pos - 1; m >= 0; --m) {
+                const u32 km = skeys[(m % EPL) * 32 + m / EPL];
+                if ((km >> 10) != r) break;
+                const double xm = px[km & 1023u];
+                less += xm < xs;
+                greater += xm > xs;
+                rs = m;
+            }
+            for (int m = pos + 1; m < cnt; ++m) {
+                const u32 km = skeys[(m % EPL) * 32 + m / EPL];
+                if ((km >> 10) != r) break;
+                const double xm = px[km & 1023u];
+                less += xm < xs;
+                greater += xm > xs;
+                re = m + 1;
             }
             sres[slot] = (u32)(rs + less) | ((u32)(re - greater) << 16);
         }
@@ -389,24 +454,24 @@ __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u
 #pragma unroll 1
     for (int s = lane; s < cnt; s += 32) {
         const u32 res = sres[s];
-        const i64 b = base + (i64)(res & 0xffffu);
-        const i64 a = o.n - base - (i64)(res >> 16);
-        emit_rank(o, row_global, pj[s], b, a);
+        emit_rank(o, row_global, pj[s], base + (res & 0xffffu), n32 - base - (res >> 16));
     }
     __syncwarp();
 }
 
-constexpr int RANK_WARPS = 4;  // 2 x 4 KB of shared scratch per warp -> 32 KB static per CTA
+constexpr int RANK_WARPS = 4;
 
-__global__ void __launch_bounds__(RANK_WARPS * 32) mbd_rank_kernel(const int P, const i64 nwarps,
-                                                                   const int *__restrict__ cursor,
-                                                                   const int *__restrict__ rowflag,
-                                                                   const double *__restrict__ part_x,
-                                                                   const u32 *__restrict__ part_j,
-                                                                   const i64 row_stride, const i64 row0,
-                                                                   const RankOut o) {
-    __shared__ u32 s_keys[RANK_WARPS][CAP];
-    __shared__ u32 s_res[RANK_WARPS][CAP];
+// One warp per (row, part).  Two instantiations share the work by part size so that the common case
+// (<= 512 values, 8 or 16 keys per lane) is not held to the register and shared-memory budget of the
+// rare 1024-value case: BIG = false ranks parts with cnt <= 512, BIG = true the others.
+template <bool BIG>
+__global__ void __launch_bounds__(RANK_WARPS * 32, BIG ? 4 : 8) mbd_rank_kernel(
+    const int P, const i64 nwarps, const int *__restrict__ cursor, const int *__restrict__ rowflag,
+    const double *__restrict__ splitters, const double *__restrict__ part_x, const u32 *__restrict__ part_j,
+    const i64 row_stride, const i64 row0, const RankOut o) {
+    constexpr int SLOTS = BIG ? CAP : CAP / 2;
+    __shared__ u32 s_keys[RANK_WARPS][SLOTS];
+    __shared__ u32 s_res[RANK_WARPS][SLOTS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const i64 w = (i64)blockIdx.x * RANK_WARPS + wid;
     if (w >= nwarps) return;
@@ -415,16 +480,27 @@ __global__ void __launch_bounds__(RANK_WARPS * 32) mbd_rank_kernel(const int P, 
     if (rowflag[row]) return;  // the whole row goes to the generic path
     const int *cur = cursor + row * P;
     const int cnt = cur[part];
-    if (cnt == 0) return;
-    i64 base = 0;
-    for (int p = lane; p < part; p += 32) base += cur[p];
+    if (cnt == 0 || (cnt > CAP / 2) != BIG) return;
+    u32 base = 0;
+    for (int p = lane; p < part; p += 32) base += (u32)cur[p];
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) base += __shfl_xor_sync(0xffffffffu, base, s);
+    // interior parts: [splitter[part-1], splitter[part]) bounds every value of the part exactly
+    const bool have_range = part > 0 && part < P - 1;
+    double lo = 0.0, hi = 0.0;
+    if (have_range) {
+        lo = splitters[row * (P - 1) + part - 1];
+        hi = splitters[row * (P - 1) + part];
+    }
     const double *px = part_x + row * row_stride + (i64)part * CAP;
     const u32 *pj = part_j + row * row_stride + (i64)part * CAP;
-    if (cnt <= 256) rank_part<8>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
-    else if (cnt <= 512) rank_part<16>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
-    else rank_part<32>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane);
+    if (BIG) {
+        rank_part<32>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane, lo, hi, have_range);
+    } else if (cnt <= 256) {
+        rank_part<8>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane, lo, hi, have_range);
+    } else {
+        rank_part<16>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane, lo, hi, have_range);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -537,7 +613,7 @@ __global__ void __launch_bounds__(1024) mbd_fallback_kernel(const double *__rest
             const i64 mid = (lo + hi) >> 1;
             if (keys[mid] <= key) lo = mid + 1; else hi = mid;
         }
-        emit_rank(o, row0 + row, (u32)c, b, n - lo);
+        emit_rank(o, row0 + row, (u32)c, (u32)b, (u32)(n - lo));
     }
 }
 
@@ -572,13 +648,13 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     if (want_j3) SD_CUDA(cudaMemsetAsync(d_acc3, 0, (size_t)n * sizeof(i64), st));
     if (T == 0) return SD_OK;
 
-    int P = n <= 512 ? 1 : (int)ceil_div(n, TARGET_PART);
+    int P = n <= CAP ? 1 : (int)ceil_div(n, TARGET_PART);  // n <= 1024: one part, one warp ranks the whole row
     if (P > MAX_PARTS) P = MAX_PARTS;
     int S = 0;
-    if (P > 1) {
+    if (P > 1) {  // n > 1024 here, so S <= n
         S = pow2ceil_int((i64)OVERSAMPLE * P);
+        if (S < 1024) S = 1024;
         if (S > MAX_SAMPLE) S = MAX_SAMPLE;
-        while (S > n) S >>= 1;
     }
     const i64 NP = pow2ceil_int(n);
     const i64 row_stride = (i64)P * CAP > NP ? (i64)P * CAP : NP;  // 8-byte slots per row
@@ -601,8 +677,6 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     double *splitters = ctx->buf[BUF_SPLIT].as<double>();
     int *fb_count = ctx->d_status + 1;
 
-    SD_CUDA(cudaFuncSetAttribute(mbd_splitters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 MAX_SAMPLE * (int)sizeof(double)));
     SD_CUDA(cudaFuncSetAttribute(mbd_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
 
     RankOut o;
@@ -624,8 +698,8 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             SD_CUDA(cudaMemsetAsync(cursor, 0, (size_t)Tc * (P + 1) * sizeof(int), st));
             if (P > 1) {
                 SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SPLITTERS));
-                mbd_splitters_kernel<<<(unsigned)rows, 512, (size_t)S * sizeof(double), st>>>(
-                    Xb, n, ld, P, S, splitters, ctx->d_status);
+                mbd_splitters_kernel<<<(unsigned)rows, SP_THREADS, 0, st>>>(Xb, n, ld, P, S, splitters,
+                                                                            ctx->d_status);
                 SD_TRY(prof_end(ctx));
                 ctx->last.launches++;
             }
@@ -637,10 +711,13 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             ctx->last.launches++;
             const i64 nwarps = rows * P;
             SD_TRY(prof_begin(ctx, SD_PHASE_MBD_RANK));
-            mbd_rank_kernel<<<(unsigned)ceil_div(nwarps, RANK_WARPS), RANK_WARPS * 32, 0, st>>>(
-                P, nwarps, cursor, rowflag, part_x, part_j, row_stride, r0, o);
+            const unsigned rgrid = (unsigned)ceil_div(nwarps, RANK_WARPS);
+            mbd_rank_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(P, nwarps, cursor, rowflag, splitters, part_x,
+                                                                    part_j, row_stride, r0, o);
+            mbd_rank_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(P, nwarps, cursor, rowflag, splitters, part_x,
+                                                                   part_j, row_stride, r0, o);
             SD_TRY(prof_end(ctx));
-            ctx->last.launches++;
+            ctx->last.launches += 2;
         }
         // rows flagged as overflowing (or all rows when forced): generic path; idle CTAs exit at once
         SD_TRY(prof_begin(ctx, SD_PHASE_MBD_GENERIC));
