@@ -136,6 +136,7 @@ __device__ __forceinline__ int sp_swz(int g) { return g ^ ((g >> 5) & 31); }
 
 __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double *__restrict__ X, i64 n, i64 ld,
                                                                    int P, int S, double *__restrict__ splitters,
+                                                                   float *__restrict__ splitters_f,
                                                                    int *__restrict__ status) {
     __shared__ u32 skey[MAX_SAMPLE];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -185,9 +186,15 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
         for (int i = 0; i < 32; ++i) skey[sp_swz(wid * 1024 + lane * 32 + i)] = v[i];
     }
     __syncthreads();
+    // splitter p as a float offset from x[0] (what the partition compares) and as a double value (the
+    // range bound the rank kernel scales its keys with)
     double *out = splitters + (i64)blockIdx.x * (P - 1);
-    for (int p = tid + 1; p < P; p += SP_THREADS)
-        out[p - 1] = x0 + (double)f32_unsortable(skey[sp_swz((int)(((i64)p * S) / P))]);
+    float *outf = splitters_f + (i64)blockIdx.x * (P - 1);
+    for (int p = tid + 1; p < P; p += SP_THREADS) {
+        const float f = f32_unsortable(skey[sp_swz((int)(((i64)p * S) / P))]);
+        outf[p - 1] = f;
+        out[p - 1] = x0 + (double)f;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -200,37 +207,69 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
 constexpr int PT_THREADS = 256;
 constexpr int PT_EPT = 16;                      // values per thread
 constexpr int PT_CHUNK = PT_THREADS * PT_EPT;   // 4096 values per CTA
-constexpr size_t PT_SMEM = (size_t)PT_CHUNK * 8 + (size_t)MAX_PARTS * 8 + (size_t)PT_CHUNK * 4 +
-                           (size_t)MAX_PARTS * 4 * 2 + (size_t)PT_CHUNK * 2 + 64;
+constexpr int PT_BUCKETS = 1024;                // equal-width lookup table over the splitter range
+constexpr size_t PT_SMEM = (size_t)PT_CHUNK * 8 + (size_t)PT_CHUNK * 4 + (size_t)MAX_PARTS * 4 * 3 +
+                           (size_t)(PT_BUCKETS + 8) * 2 + 64;
+
+// part of a value = number of splitters <= f, f = float(x - x[0]).  Every step is monotone in x, so
+// equal values share a part and parts are ordered.  The lookup table only provides a starting guess
+// (first splitter of the value's equal-width bucket); the two short scans make the result exact.
+__device__ __forceinline__ int part_of(const float f, const float *__restrict__ splf, const int nspl,
+                                       const unsigned short *__restrict__ tbl, const float f_first,
+                                       const float inv_w) {
+    float fb = (f - f_first) * inv_w;
+    fb = fminf(fmaxf(fb, 0.f), (float)(PT_BUCKETS - 1));  // also maps NaN (inf * 0) to 0
+    int idx = tbl[(int)fb];
+    while (idx > 0 && splf[idx - 1] > f) --idx;
+    while (idx < nspl && splf[idx] <= f) ++idx;
+    return idx;
+}
 
 __global__ void __launch_bounds__(PT_THREADS) mbd_partition_kernel(const double *__restrict__ X, i64 n, i64 ld, int P,
-                                                                   const double *__restrict__ splitters,
+                                                                   const float *__restrict__ splitters_f,
                                                                    int *__restrict__ cursor, int *__restrict__ rowflag,
                                                                    double *__restrict__ part_x,
                                                                    u32 *__restrict__ part_j, i64 row_stride,
                                                                    int *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char pt_smem[];
     double *sx = reinterpret_cast<double *>(pt_smem);                 // grouped values
-    double *spl = sx + PT_CHUNK;                                      // splitters of this row
-    u32 *sj = reinterpret_cast<u32 *>(spl + MAX_PARTS);               // grouped curve ids
-    int *pre = reinterpret_cast<int *>(sj + PT_CHUNK);                // per-part count, then exclusive prefix
+    u32 *sj = reinterpret_cast<u32 *>(sx + PT_CHUNK);                 // grouped (part << 12 | index in chunk)
+    float *splf = reinterpret_cast<float *>(sj + PT_CHUNK);           // splitters of this row (float offsets)
+    int *pre = reinterpret_cast<int *>(splf + MAX_PARTS);             // per-part count, then exclusive prefix
     int *off = pre + MAX_PARTS;                                       // global slot base - prefix
-    unsigned short *sp = reinterpret_cast<unsigned short *>(off + MAX_PARTS);  // part of grouped position
-    int *wtot = reinterpret_cast<int *>(sp + PT_CHUNK);               // warp totals of the scan
+    unsigned short *tbl = reinterpret_cast<unsigned short *>(off + MAX_PARTS);  // bucket -> first splitter
+    int *wtot = reinterpret_cast<int *>(tbl + PT_BUCKETS + 8);        // warp totals of the scan
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int row = blockIdx.y;
     const double *xr = X + (i64)row * ld;
+    const double x0 = xr[0];
     const int nspl = P - 1;
-    for (int i = tid; i < nspl; i += PT_THREADS) spl[i] = splitters[(i64)row * nspl + i];
+    for (int i = tid; i < nspl; i += PT_THREADS) splf[i] = splitters_f[(i64)row * nspl + i];
     for (int i = tid; i < P; i += PT_THREADS) pre[i] = 0;
     __syncthreads();
-    int top = 1;
-    while (top < P) top <<= 1;
+    float f_first = 0.f, inv_w = 0.f;
+    if (nspl > 0) {
+        f_first = splf[0];
+        const float w = (splf[nspl - 1] - f_first) * (1.0f / PT_BUCKETS);
+        if (w > 0.f && w < INFINITY) inv_w = 1.0f / w;
+        int top = 1;
+        while (top < P) top <<= 1;
+        for (int b = tid; b < PT_BUCKETS; b += PT_THREADS) {  // tbl[b] = #splitters < lower edge of bucket b
+            const float edge = f_first + (float)b * w;
+            int lo = 0;
+            for (int step = top >> 1; step > 0; step >>= 1) {
+                const int probe = lo + step;
+                if (probe <= nspl && splf[probe - 1] < edge) lo = probe;
+            }
+            tbl[b] = (unsigned short)(inv_w > 0.f ? lo : 0);
+        }
+    }
+    __syncthreads();
     const i64 c0 = (i64)blockIdx.x * PT_CHUNK;
     const int len = (n - c0) < PT_CHUNK ? (int)(n - c0) : PT_CHUNK;
 
-    // A. load, locate the part (number of splitters <= x), claim a position inside the CTA's group
+    // A. load, locate the part, claim a position inside the CTA's group (shared-memory atomic)
     double x[PT_EPT];
     u32 tag[PT_EPT];  // part << 16 | position within (CTA, part)
     bool bad = false;
@@ -241,19 +280,12 @@ __global__ void __launch_bounds__(PT_THREADS) mbd_partition_kernel(const double 
         bad |= !isfinite(x[u]);
     }
 #pragma unroll
-    for (int u0 = 0; u0 < PT_EPT; u0 += 4) {
-        int lo[4] = {0, 0, 0, 0};
-        for (int step = top >> 1; step > 0; step >>= 1) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int probe = lo[u] + step;
-                if (probe <= nspl && spl[probe - 1] <= x[u0 + u]) lo[u] = probe;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = (u0 + u) * PT_THREADS + tid;
-            tag[u0 + u] = i < len ? ((u32)lo[u] << 16) | (u32)atomicAdd(&pre[lo[u]], 1) : 0xffffffffu;
+    for (int u = 0; u < PT_EPT; ++u) {
+        const int i = u * PT_THREADS + tid;
+        tag[u] = 0xffffffffu;
+        if (i < len) {
+            const int part = nspl > 0 ? part_of(__double2float_rn(x[u] - x0), splf, nspl, tbl, f_first, inv_w) : 0;
+            tag[u] = ((u32)part << 16) | (u32)atomicAdd(&pre[part], 1);
         }
     }
     if (bad) atomicOr(status, ST_NONFINITE);
@@ -302,8 +334,7 @@ __global__ void __launch_bounds__(PT_THREADS) mbd_partition_kernel(const double 
             const int part = (int)(tag[u] >> 16);
             const int pos = pre[part] + (int)(tag[u] & 0xffffu);
             sx[pos] = x[u];
-            sj[pos] = (u32)(c0 + u * PT_THREADS + tid);
-            sp[pos] = (unsigned short)part;
+            sj[pos] = ((u32)part << 12) | (u32)(u * PT_THREADS + tid);
         }
     }
     __syncthreads();
@@ -312,12 +343,13 @@ __global__ void __launch_bounds__(PT_THREADS) mbd_partition_kernel(const double 
     double *px = part_x + (i64)row * row_stride;
     u32 *pj = part_j + (i64)row * row_stride;
     for (int i = tid; i < len; i += PT_THREADS) {
-        const int part = sp[i];
+        const u32 t = sj[i];
+        const int part = (int)(t >> 12);
         const int slot = off[part] + i;
         if (slot < CAP) {
             const i64 at = (i64)part * CAP + slot;
             px[at] = sx[i];
-            pj[at] = sj[i];
+            pj[at] = (u32)(c0 + (t & 4095u));
         }
     }
 }
@@ -669,12 +701,13 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     SD_TRY(ctx->buf[BUF_PART_X].reserve((size_t)Tc * row_stride * 8));
     SD_TRY(ctx->buf[BUF_PART_J].reserve((size_t)Tc * row_stride * 4));
     SD_TRY(ctx->buf[BUF_CURSOR].reserve((size_t)Tc * (P + 1) * sizeof(int)));
-    SD_TRY(ctx->buf[BUF_SPLIT].reserve((size_t)Tc * (P > 1 ? P - 1 : 1) * sizeof(double)));
+    SD_TRY(ctx->buf[BUF_SPLIT].reserve((size_t)Tc * (P > 1 ? P - 1 : 1) * (sizeof(double) + sizeof(float))));
     double *part_x = ctx->buf[BUF_PART_X].as<double>();
     u32 *part_j = ctx->buf[BUF_PART_J].as<u32>();
     int *cursor = ctx->buf[BUF_CURSOR].as<int>();
     int *rowflag = cursor + (size_t)Tc * P;
     double *splitters = ctx->buf[BUF_SPLIT].as<double>();
+    float *splitters_f = reinterpret_cast<float *>(splitters + (size_t)Tc * (P > 1 ? P - 1 : 1));
     int *fb_count = ctx->d_status + 1;
 
     SD_CUDA(cudaFuncSetAttribute(mbd_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
@@ -698,15 +731,15 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             SD_CUDA(cudaMemsetAsync(cursor, 0, (size_t)Tc * (P + 1) * sizeof(int), st));
             if (P > 1) {
                 SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SPLITTERS));
-                mbd_splitters_kernel<<<(unsigned)rows, SP_THREADS, 0, st>>>(Xb, n, ld, P, S, splitters,
+                mbd_splitters_kernel<<<(unsigned)rows, SP_THREADS, 0, st>>>(Xb, n, ld, P, S, splitters, splitters_f,
                                                                             ctx->d_status);
                 SD_TRY(prof_end(ctx));
                 ctx->last.launches++;
             }
             dim3 pgrid((unsigned)ceil_div(n, PT_CHUNK), (unsigned)rows);
             SD_TRY(prof_begin(ctx, SD_PHASE_MBD_PARTITION));
-            mbd_partition_kernel<<<pgrid, PT_THREADS, PT_SMEM, st>>>(Xb, n, ld, P, splitters, cursor, rowflag, part_x,
-                                                                     part_j, row_stride, ctx->d_status);
+            mbd_partition_kernel<<<pgrid, PT_THREADS, PT_SMEM, st>>>(Xb, n, ld, P, splitters_f, cursor, rowflag,
+                                                                     part_x, part_j, row_stride, ctx->d_status);
             SD_TRY(prof_end(ctx));
             ctx->last.launches++;
             const i64 nwarps = rows * P;
