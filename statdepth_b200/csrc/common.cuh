@@ -62,6 +62,7 @@ enum BufId {
     BUF_MASK,       // strict BD: per-query sign masks
     BUF_MISC,       // small odds and ends
     BUF_AUX,        // batched / extra
+    BUF_WORK,       // MBD: work list of big parts
     NUM_BUFS
 };
 

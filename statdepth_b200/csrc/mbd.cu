@@ -23,6 +23,8 @@
 //                             finite input; ~3x slower.
 // HBM layout: X[t*ld + c] float64 (time-major rows are contiguous and streamed with coalesced
 // loads); acc int64[n]; part lists [row][part][CAP] float64 + uint32.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sd {
@@ -496,42 +498,75 @@ constexpr int RANK_WARPS = 4;
 // One warp per (row, part).  Two instantiations share the work by part size so that the common case
 // (<= 512 values, 8 or 16 keys per lane) is not held to the register and shared-memory budget of the
 // rare 1024-value case: BIG = false ranks parts with cnt <= 512, BIG = true the others.
-template <bool BIG>
-__global__ void __launch_bounds__(RANK_WARPS * 32, BIG ? 4 : 8) mbd_rank_kernel(
-    const int P, const i64 nwarps, const int *__restrict__ cursor, const int *__restrict__ rowflag,
-    const double *__restrict__ splitters, const double *__restrict__ part_x, const u32 *__restrict__ part_j,
-    const i64 row_stride, const i64 row0, const RankOut o) {
-    constexpr int SLOTS = BIG ? CAP : CAP / 2;
-    __shared__ u32 s_keys[RANK_WARPS][SLOTS];
-    __shared__ u32 s_res[RANK_WARPS][SLOTS];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const i64 w = (i64)blockIdx.x * RANK_WARPS + wid;
-    if (w >= nwarps) return;
-    const i64 row = w / P;
-    const int part = (int)(w - row * P);
-    if (rowflag[row]) return;  // the whole row goes to the generic path
-    const int *cur = cursor + row * P;
-    const int cnt = cur[part];
-    if (cnt == 0 || (cnt > CAP / 2) != BIG) return;
+struct RankArgs {
+    int P;
+    i64 nwarps;                // rows * P
+    const int *cursor;         // [rows][P] fill counts
+    const int *rowflag;        // [rows] 1 = row overflowed, generic path takes it
+    const double *splitters;   // [rows][P-1]
+    const double *part_x;      // [rows][row_stride]
+    const u32 *part_j;
+    i64 row_stride, row0;
+    int2 *biglist;             // (row, part) of parts with more than CAP/2 values
+    int *bigcount;             // [0] entries appended, [1] entries claimed
+};
+
+template <int EPL>
+__device__ __forceinline__ void rank_one(const RankArgs &a, const RankOut &o, const i64 row, const int part,
+                                         const int cnt, u32 *skeys, u32 *sres, const int lane) {
+    const int P = a.P;
+    const int *cur = a.cursor + row * P;
     u32 base = 0;
     for (int p = lane; p < part; p += 32) base += (u32)cur[p];
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) base += __shfl_xor_sync(0xffffffffu, base, s);
-    // interior parts: [splitter[part-1], splitter[part]) bounds every value of the part exactly
+    // interior parts: [splitter[part-1], splitter[part]) bounds the values of the part
     const bool have_range = part > 0 && part < P - 1;
     double lo = 0.0, hi = 0.0;
     if (have_range) {
-        lo = splitters[row * (P - 1) + part - 1];
-        hi = splitters[row * (P - 1) + part];
+        lo = a.splitters[row * (P - 1) + part - 1];
+        hi = a.splitters[row * (P - 1) + part];
     }
-    const double *px = part_x + row * row_stride + (i64)part * CAP;
-    const u32 *pj = part_j + row * row_stride + (i64)part * CAP;
-    if (BIG) {
-        rank_part<32>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane, lo, hi, have_range);
-    } else if (cnt <= 256) {
-        rank_part<8>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane, lo, hi, have_range);
-    } else {
-        rank_part<16>(px, pj, cnt, base, row0 + row, o, s_keys[wid], s_res[wid], lane, lo, hi, have_range);
+    const double *px = a.part_x + row * a.row_stride + (i64)part * CAP;
+    const u32 *pj = a.part_j + row * a.row_stride + (i64)part * CAP;
+    rank_part<EPL>(px, pj, cnt, base, a.row0 + row, o, skeys, sres, lane, lo, hi, have_range);
+}
+
+// One warp per (row, part) for parts of at most CAP/2 values (8 or 16 keys per lane, 56 registers);
+// bigger parts are appended to a work list for mbd_rank_big_kernel so that the common case is not held
+// to the register / shared-memory budget of the rare 1024-value case.
+__global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_kernel(const RankArgs a, const RankOut o) {
+    __shared__ u32 s_keys[RANK_WARPS][CAP / 2];
+    __shared__ u32 s_res[RANK_WARPS][CAP / 2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const i64 w = (i64)blockIdx.x * RANK_WARPS + wid;
+    if (w >= a.nwarps) return;
+    const i64 row = w / a.P;
+    const int part = (int)(w - row * a.P);
+    if (a.rowflag[row]) return;  // the whole row goes to the generic path
+    const int cnt = a.cursor[row * a.P + part];
+    if (cnt == 0) return;
+    if (cnt > CAP / 2) {
+        if (lane == 0) a.biglist[atomicAdd(&a.bigcount[0], 1)] = make_int2((int)row, part);
+        return;
+    }
+    if (cnt <= 256) rank_one<8>(a, o, row, part, cnt, s_keys[wid], s_res[wid], lane);
+    else rank_one<16>(a, o, row, part, cnt, s_keys[wid], s_res[wid], lane);
+}
+
+// persistent: warps claim entries of the big-part work list
+__global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const RankArgs a, const RankOut o) {
+    __shared__ u32 s_keys[RANK_WARPS][CAP];
+    __shared__ u32 s_res[RANK_WARPS][CAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int total = a.bigcount[0];
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&a.bigcount[1], 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= total) break;
+        const int2 e = a.biglist[i];
+        rank_one<32>(a, o, (i64)e.x, e.y, a.cursor[(i64)e.x * a.P + e.y], s_keys[wid], s_res[wid], lane);
     }
 }
 
@@ -680,7 +715,12 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     if (want_j3) SD_CUDA(cudaMemsetAsync(d_acc3, 0, (size_t)n * sizeof(i64), st));
     if (T == 0) return SD_OK;
 
-    int P = n <= CAP ? 1 : (int)ceil_div(n, TARGET_PART);  // n <= 1024: one part, one warp ranks the whole row
+    int target = TARGET_PART;
+    if (const char *e = getenv("SD_MBD_TARGET_PART")) {  // tuning aid
+        const int v = atoi(e);
+        if (v >= 64 && v <= 512) target = v;
+    }
+    int P = n <= CAP ? 1 : (int)ceil_div(n, target);  // n <= 1024: one part, one warp ranks the whole row
     if (P > MAX_PARTS) P = MAX_PARTS;
     int S = 0;
     if (P > 1) {  // n > 1024 here, so S <= n
@@ -709,6 +749,8 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     double *splitters = ctx->buf[BUF_SPLIT].as<double>();
     float *splitters_f = reinterpret_cast<float *>(splitters + (size_t)Tc * (P > 1 ? P - 1 : 1));
     int *fb_count = ctx->d_status + 1;
+    SD_TRY(ctx->buf[BUF_WORK].reserve((size_t)Tc * P * sizeof(int2)));
+    int2 *biglist = ctx->buf[BUF_WORK].as<int2>();
 
     SD_CUDA(cudaFuncSetAttribute(mbd_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
 
@@ -744,11 +786,21 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             ctx->last.launches++;
             const i64 nwarps = rows * P;
             SD_TRY(prof_begin(ctx, SD_PHASE_MBD_RANK));
-            const unsigned rgrid = (unsigned)ceil_div(nwarps, RANK_WARPS);
-            mbd_rank_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(P, nwarps, cursor, rowflag, splitters, part_x,
-                                                                    part_j, row_stride, r0, o);
-            mbd_rank_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(P, nwarps, cursor, rowflag, splitters, part_x,
-                                                                   part_j, row_stride, r0, o);
+            RankArgs ra;
+            ra.P = P;
+            ra.nwarps = nwarps;
+            ra.cursor = cursor;
+            ra.rowflag = rowflag;
+            ra.splitters = splitters;
+            ra.part_x = part_x;
+            ra.part_j = part_j;
+            ra.row_stride = row_stride;
+            ra.row0 = r0;
+            ra.biglist = biglist;
+            ra.bigcount = ctx->d_status + 2;
+            SD_CUDA(cudaMemsetAsync(ctx->d_status + 2, 0, 2 * sizeof(int), st));
+            mbd_rank_kernel<<<(unsigned)ceil_div(nwarps, RANK_WARPS), RANK_WARPS * 32, 0, st>>>(ra, o);
+            mbd_rank_big_kernel<<<(unsigned)(ctx->sm_count * 4), RANK_WARPS * 32, 0, st>>>(ra, o);
             SD_TRY(prof_end(ctx));
             ctx->last.launches += 2;
         }
