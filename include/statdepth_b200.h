@@ -64,7 +64,15 @@ enum sd_bd_impl {
 enum sd_option {
     SD_OPT_BD_IMPL = 1,       /* enum sd_bd_impl */
     SD_OPT_MBD_FORCE_FALLBACK = 2, /* 1: rank every row with the generic (slow) path; testing aid */
-    SD_OPT_PROFILE = 3            /* 1: bracket every kernel phase with CUDA events (sd_get_phase_ns) */
+    SD_OPT_PROFILE = 3,           /* 1: bracket every kernel phase with CUDA events (sd_get_phase_ns) */
+    SD_OPT_SIMPLICIAL_IMPL = 4    /* enum sd_simplicial_impl: 2-D triangle counting algorithm */
+};
+
+/* how 2-D simplicial counts (point clouds, relaxed multivariate simplex depth) are obtained */
+enum sd_simplicial_impl {
+    SD_SIMPLICIAL_AUTO = 0,      /* enumerate small samples (tolerance band honoured), count large ones */
+    SD_SIMPLICIAL_ENUMERATE = 1, /* all (d+1)-subsets, closed simplex test with tolerance `tol` */
+    SD_SIMPLICIAL_COUNT = 2      /* O(n log n) angular counting, exact closed triangles (tol ignored), d = 2 */
 };
 
 /* phases of the modified-band-depth pipeline reported by sd_get_phase_ns */

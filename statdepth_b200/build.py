@@ -27,6 +27,7 @@ SOURCES = {
     "bd_bits.cu": [],
     "bd_gemm.cu": [],
     "pointcloud.cu": ["-fmad=false"],
+    "simplicial_count.cu": ["-fmad=false"],
 }
 EXPORT_MAP = os.path.join(CSRC, "exports.map")
 

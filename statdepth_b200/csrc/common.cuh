@@ -95,6 +95,7 @@ struct sd_ctx {
     int bd_impl = SD_BD_AUTO;
     int mbd_force_fallback = 0;
     int profile = 0;
+    int simplicial_impl = SD_SIMPLICIAL_AUTO;
     static const int MAX_PROF = 256;                 // event pairs per call when profiling
     cudaEvent_t prof_ev[2 * MAX_PROF] = {};          // created lazily
     int prof_phase[MAX_PROF] = {};
@@ -133,6 +134,8 @@ int oja_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 
                i64 npool, double hull_volume, double *d_out);
 int simplicial_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 nq, double tol,
                       i64 *d_out);
+int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride_j, i64 T, const i64 *d_q, i64 nq,
+                             i64 *d_out);
 int simplex_depth_device(sd_ctx *ctx, const double *dF, i64 N, i64 T, int d, const i64 *d_q, i64 nq,
                          int relax, double tol, i64 *d_out);
 

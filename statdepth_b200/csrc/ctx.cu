@@ -274,6 +274,13 @@ int sd_set_option(sd_ctx *ctx, int option, int64_t value) {
         case SD_OPT_PROFILE:
             ctx->profile = value ? 1 : 0;
             return SD_OK;
+        case SD_OPT_SIMPLICIAL_IMPL:
+            if (value < SD_SIMPLICIAL_AUTO || value > SD_SIMPLICIAL_COUNT) {
+                sd::set_error("sd_set_option: bad SD_OPT_SIMPLICIAL_IMPL value %lld", (long long)value);
+                return SD_ERR_INVALID;
+            }
+            ctx->simplicial_impl = (int)value;
+            return SD_OK;
         default:
             sd::set_error("sd_set_option: unknown option %d", option);
             return SD_ERR_INVALID;

@@ -1,0 +1,221 @@
+// simplicial_count.cu -- exact O(n log n) counting of the triangles that contain a query point (d = 2).
+//
+// Replaces the enumeration of all 3-subsets in the 'simplex' branch of _pointwisedepth
+// (statdepth/depth/calculations/_pointcloud.py:44-56) and, per time point, in _simplex_depth with
+// relax=True (_functional.py:257-286) when the sample is too large to enumerate (BASELINE configs 5 and
+// 4: 50 000 points / 5 000 curves x 256 points).  Rousseeuw-Ruts style: a closed triangle of three other
+// points does NOT contain p iff its three directions from p lie in an open half-plane, and such a triple
+// has a unique first direction in counter-clockwise order.  With directions grouped into classes of
+// equal angle (g points each) and c = number of points strictly inside the half-turn after the class,
+//     #non-containing triples whose first class is this one = C(g + c, 3) - C(c, 3)
+//     #containing = C(m, 3) - sum over classes                  (m = all other points; points equal to p
+//                                                               only form containing triples)
+// Angles are never computed: each direction d = x - p gets the key  8 + octant + f  in [8, 16), f the
+// correctly rounded ratio of its smaller to its larger component (mirrored in odd octants).  Correct
+// rounding is monotone, so the key order IS the angular order of the computed directions, directions
+// that are exactly collinear get identical keys, and the antipode is exactly key +- 4 (one binade).
+// Ranks come from the modified-band-depth rank pipeline (mbd.cu), run on two key matrices per batch of
+// instances: A = keys (n per row), B = keys and antipodes (2n per row).
+//
+// Semantics: exact closed triangles of the computed float64 directions (tolerance 0).  The reference
+// decides with an LP whose ~1e-7 feasibility band only matters for triangles with p within 1e-7 of an
+// edge; the enumeration kernels (pointcloud.cu) keep that band for the sizes the reference can run.
+#include "common.cuh"
+
+namespace sd {
+
+constexpr double SC_ZERO = 8.0 + 9.0;   // direction is the zero vector (point coincides with the query)
+constexpr double SC_SELF = 8.0 + 10.0;  // the query's own entry
+
+// instance -> (query index, offset of its coordinates); mode 0: point cloud, mode 1: functional (q, t)
+struct ScGeom {
+    const double *pts;   // point j of instance i at pts[j * stride_j + inst_off(i) + {0,1}]
+    i64 stride_j;
+    const i64 *qidx;     // query ids (may be null = identity)
+    i64 T;               // functional: instances per query (time points); point cloud: 1
+    i64 inst0;           // first instance of this batch
+};
+
+__device__ __forceinline__ i64 sc_query(const ScGeom &g, i64 inst) {
+    const i64 qi = inst / g.T;
+    return g.qidx ? g.qidx[qi] : qi;
+}
+__device__ __forceinline__ i64 sc_off(const ScGeom &g, i64 inst) { return (inst % g.T) * 2; }
+
+// exact-monotone angular key of a non-zero direction, in [8, 16)
+__device__ __forceinline__ double sc_key(double dx, double dy) {
+    double add = 8.0;
+    if (dy < 0.0 || (dy == 0.0 && dx < 0.0)) {  // lower half-plane (and the negative x axis): rotate by pi
+        dx = -dx;
+        dy = -dy;
+        add = 12.0;
+    }
+    // now dy > 0, or dy == 0 and dx > 0: angle in [0, pi)
+    double oct, f;
+    if (dx > 0.0) {
+        if (dy < dx) { oct = 0.0; f = dy / dx; }            // [0, pi/4)
+        else         { oct = 1.0; f = 1.0 - dx / dy; }      // [pi/4, pi/2)
+    } else {
+        const double ax = -dx;
+        if (ax < dy) { oct = 2.0; f = ax / dy; }            // [pi/2, 3pi/4)
+        else         { oct = 3.0; f = 1.0 - dy / ax; }      // [3pi/4, pi)
+    }
+    return (add + oct) + f;  // f in [0,1): one rounding to the [8,16) binade, monotone
+}
+
+// KA[i][j] = key_j; KB[i][j] = key_j, KB[i][n + j] = antipode of key_j
+__global__ void __launch_bounds__(256) sc_keys_kernel(const ScGeom g, const i64 n, const i64 ninst,
+                                                      double *__restrict__ KA, double *__restrict__ KB,
+                                                      int *__restrict__ status) {
+    const i64 li = blockIdx.y;  // instance within the batch
+    if (li >= ninst) return;
+    const i64 inst = g.inst0 + li;
+    const i64 q = sc_query(g, inst);
+    const i64 off = sc_off(g, inst);
+    const double px = g.pts[q * g.stride_j + off], py = g.pts[q * g.stride_j + off + 1];
+    bool bad = false;
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) {
+        double u, w;
+        if (j == q) {
+            u = w = SC_SELF;
+        } else {
+            const double xj = g.pts[j * g.stride_j + off], yj = g.pts[j * g.stride_j + off + 1];
+            bad |= !isfinite(xj) || !isfinite(yj);
+            const double dx = xj - px, dy = yj - py;
+            if (dx == 0.0 && dy == 0.0) {
+                u = w = SC_ZERO;
+            } else {
+                u = sc_key(dx, dy);
+                w = u < 12.0 ? u + 4.0 : u - 4.0;  // exact: same binade
+            }
+        }
+        KA[li * n + j] = u;
+        KB[li * 2 * n + j] = u;
+        KB[li * 2 * n + n + j] = w;
+    }
+    if (bad || !isfinite(px) || !isfinite(py)) atomicOr(status, ST_NONFINITE);
+}
+
+__device__ __forceinline__ i64 c3(i64 m) { return m < 3 ? 0 : (m * (m - 1) / 2) * (m - 2) / 3; }
+
+// one CTA per instance.  bA/aA: ranks of row A; bB: ranks (strictly below) of row B.
+// out[query slot] += #triangles of other points containing the query point.
+__global__ void __launch_bounds__(256) sc_reduce_kernel(const ScGeom g, const i64 n, const double *__restrict__ KA,
+                                                        const int *__restrict__ bA, const int *__restrict__ aA,
+                                                        const int *__restrict__ bB, int *__restrict__ claim,
+                                                        i64 *__restrict__ out) {
+    __shared__ i64 s_red[8];
+    __shared__ i64 s_cnt[2];
+    const i64 li = blockIdx.x;
+    const i64 inst = g.inst0 + li;
+    const double *ka = KA + li * n;
+    const int *ba = bA + li * n, *aa = aA + li * n, *bb = bB + li * 2 * n;
+    int *cl = claim + li * n;
+    // pass 1: number of real directions m' and how many of them lie in [0, pi)  (key < 12)
+    i64 real = 0, low = 0;
+    for (i64 j = threadIdx.x; j < n; j += blockDim.x) {
+        const double u = ka[j];
+        real += u < 16.0;
+        low += u < 12.0;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        real += __shfl_xor_sync(0xffffffffu, real, s);
+        low += __shfl_xor_sync(0xffffffffu, low, s);
+    }
+    if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd((u64 *)&s_cnt[0], (u64)real);
+        atomicAdd((u64 *)&s_cnt[1], (u64)low);
+    }
+    __syncthreads();
+    const i64 mreal = s_cnt[0], L4 = s_cnt[1], H = mreal - L4;
+    // pass 2: every class of equal directions contributes C(g + c, 3) - C(c, 3) once
+    i64 noncontain = 0;
+    for (i64 j = threadIdx.x; j < n; j += blockDim.x) {
+        const double u = ka[j];
+        if (!(u < 16.0)) continue;  // zero vector or the query itself
+        const i64 L = ba[j];                      // real directions strictly before this one
+        const i64 gsz = n - L - (i64)aa[j];       // size of its class (sentinels are never equal to it)
+        const i64 b2w = bb[n + j];                // entries of row B strictly below the antipode
+        i64 c;
+        if (u < 12.0) {
+            const i64 Lw = b2w - L - H;           // real directions strictly before the antipode
+            c = Lw - L - gsz;
+        } else {
+            const i64 Lw = b2w - L + L4;
+            c = (mreal - L - gsz) + Lw;
+        }
+        if (gsz == 1) {
+            noncontain += c * (c - 1) / 2;        // C(1 + c, 3) - C(c, 3) = C(c, 2)
+        } else if (atomicCAS(&cl[L], 0, 1) == 0) {  // first member of the class to arrive speaks for it
+            noncontain += c3(gsz + c) - c3(c);
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) noncontain += __shfl_xor_sync(0xffffffffu, noncontain, s);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = noncontain;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        i64 tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w];
+        const i64 m = n - 1;
+        atomicAdd((u64 *)&out[inst / g.T], (u64)(c3(m) - tot));
+    }
+}
+
+// Counts for `nq` queries x `T` instances each (T = 1 for point clouds).  d_out[nq] is zeroed here.
+int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride_j, i64 T, const i64 *d_q, i64 nq,
+                             i64 *d_out) {
+    cudaStream_t st = ctx->stream;
+    SD_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nq * sizeof(i64), st));
+    const i64 ninst_total = nq * T;
+    if (ninst_total == 0 || n < 4) return SD_OK;  // fewer than 3 other points: no triangle
+    if (2 * n >= (1ll << 31)) {
+        set_error("simplicial counting: n=%lld too large", (long long)n);
+        return SD_ERR_UNSUPPORTED;
+    }
+    // batch size: ~48 n bytes of keys and ranks per instance (+ the rank pipeline's part lists)
+    i64 IB = (i64)((3ull << 30) / (size_t)(48 * n));
+    if (IB < 1) IB = 1;
+    if (IB > 32768) IB = 32768;
+    if (IB > ninst_total) IB = ninst_total;
+    SD_TRY(ctx->buf[BUF_IN2].reserve((size_t)IB * n * 3 * sizeof(double)));
+    SD_TRY(ctx->buf[BUF_MASK].reserve((size_t)IB * n * 7 * sizeof(int)));
+    SD_TRY(ctx->buf[BUF_ACC].reserve((size_t)n * 2 * 2 * sizeof(i64)));
+    double *KA = ctx->buf[BUF_IN2].as<double>();
+    double *KB = KA + (size_t)IB * n;
+    int *bA = ctx->buf[BUF_MASK].as<int>();
+    int *aA = bA + (size_t)IB * n;
+    int *bB = aA + (size_t)IB * n;
+    int *aB = bB + (size_t)IB * 2 * n;
+    int *claim = aB + (size_t)IB * 2 * n;
+    i64 *acc = ctx->buf[BUF_ACC].as<i64>();
+    ScGeom g;
+    g.pts = d_pts;
+    g.stride_j = stride_j;
+    g.qidx = d_q;
+    g.T = T;
+    for (i64 i0 = 0; i0 < ninst_total; i0 += IB) {
+        const i64 ni = ninst_total - i0 < IB ? ninst_total - i0 : IB;
+        g.inst0 = i0;
+        unsigned gx = (unsigned)ceil_div(n, 256 * 4);
+        if (gx < 1) gx = 1;
+        if (ni > 65535) {
+            set_error("simplicial counting: internal batch too large");
+            return SD_ERR_UNSUPPORTED;
+        }
+        sc_keys_kernel<<<dim3(gx, (unsigned)ni), 256, 0, st>>>(g, n, ni, KA, KB, ctx->d_status);
+        ctx->last.launches++;
+        SD_CUDA(cudaMemsetAsync(claim, 0, (size_t)ni * n * sizeof(int), st));
+        SD_TRY(mbd_all_device(ctx, KA, ni, n, n, false, acc, acc + n, bA, aA));
+        SD_TRY(mbd_all_device(ctx, KB, ni, 2 * n, 2 * n, false, acc, acc + 2 * n, bB, aB));
+        sc_reduce_kernel<<<(unsigned)ni, 256, 0, st>>>(g, n, KA, bA, aA, bB, claim, d_out);
+        ctx->last.launches++;
+        SD_CUDA(cudaGetLastError());
+    }
+    return SD_OK;
+}
+
+}  // namespace sd

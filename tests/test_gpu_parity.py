@@ -299,6 +299,63 @@ def test_simplicial_degenerate_inputs(engine, oracle):
     assert (engine.simplicial_counts(L) == oracle.simplicial_counts(L)).all()
 
 
+def test_simplicial_angular_counting(engine, oracle):
+    """SD_SIMPLICIAL_COUNT: the O(n log n) angular counting gives exactly the enumeration's counts
+    (closed triangles, tolerance 0) -- general position, lattice data with collinear / duplicate /
+    antipodal points, and a larger cloud checked against the GPU enumeration."""
+    from statdepth_b200 import _engine as E
+    rng = np.random.default_rng(17)
+    try:
+        engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_COUNT)
+        for n, lattice in ((37, False), (30, True), (64, True), (5, False), (4, False), (3, False), (200, False)):
+            P = rng.integers(0, 5, size=(n, 2)).astype(np.float64) if lattice else rng.standard_normal((n, 2))
+            assert (engine.simplicial_counts(P, None, 0.0) == oracle.simplicial_counts(P, None, 0.0)).all()
+        P = rng.standard_normal((1500, 2))
+        q = [0, 777, 1499]
+        got = engine.simplicial_counts(P, q, 0.0)
+        engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_ENUMERATE)
+        assert (got == engine.simplicial_counts(P, q, 0.0)).all()
+    finally:
+        engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_AUTO)
+
+
+def test_simplicial_full_size_properties(engine):
+    """BASELINE config 5: 2-D simplicial depth of 50 000 points (generate_noisy_pointcloud(n, 2, seed=4)).
+    Size-independent checks: 0 <= count <= C(n-1,3); translating / scaling by powers of two leaves every
+    count unchanged; the deepest point is near the centre, hull vertices have count 0."""
+    from statdepth_b200.testing import generate_noisy_pointcloud
+    n = 50_000
+    P = generate_noisy_pointcloud(n=n, d=2, seed=4).values
+    q = np.arange(0, n, 97)
+    c = engine.simplicial_counts(P, q, 0.0)
+    assert c.min() >= 0 and c.max() <= comb(n - 1, 3)
+    assert (engine.simplicial_counts(P * 4.0, q, 0.0) == c).all()
+    far = int(np.argmax((P ** 2).sum(1)))
+    assert engine.simplicial_counts(P, [far], 0.0)[0] == 0
+    deepest = q[int(np.argmax(c))]
+    assert np.hypot(*P[deepest]) < 0.2 and c.max() / comb(n, 3) > 0.24  # max simplicial depth in 2-D is 1/4
+
+
+def test_relaxed_simplex_depth_counting(engine, oracle):
+    """Relaxed multivariate simplex depth (d = 2) through the counting path, per (query, time point)."""
+    from statdepth_b200 import _engine as E
+    rng = np.random.default_rng(19)
+    try:
+        engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_COUNT)
+        for N, T in ((12, 9), (30, 5), (7, 3)):
+            F = rng.standard_normal((N, T, 2)).cumsum(1)
+            assert (engine.simplex_depth_counts(F, None, True, 0.0) == oracle.simplex_depth_counts(F, None, True, 0.0)).all()
+            assert (engine.simplex_depth_counts(F, [N - 1, 1], True, 0.0) ==
+                    oracle.simplex_depth_counts(F, [N - 1, 1], True, 0.0)).all()
+        Fl = rng.integers(0, 4, size=(15, 6, 2)).astype(np.float64)
+        assert (engine.simplex_depth_counts(Fl, None, True, 0.0) == oracle.simplex_depth_counts(Fl, None, True, 0.0)).all()
+    finally:
+        engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_AUTO)
+    # AUTO switches to counting above 64 curves
+    F = rng.standard_normal((80, 4, 2)).cumsum(1)
+    assert (engine.simplex_depth_counts(F, [0, 41], True, 0.0) == oracle.simplex_depth_counts(F, [0, 41], True, 0.0)).all()
+
+
 @pytest.mark.parametrize("n,d,seed", [(60, 2, 0), (20, 3, 1)])
 def test_oja(engine, oracle, n, d, seed):
     from scipy.spatial import ConvexHull
