@@ -144,7 +144,7 @@ def run_reference(args):
     v = float(np.mean(vals))
     cb.update(value=v)
     cb.pop("seconds_sample", None)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "BD/MBD depth-evals/sec", "value": v, "unit": "depth-evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -155,11 +155,29 @@ def run_reference(args):
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "depth-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+def emit(line: dict):
+    """Print THE one JSON line on the real stdout (see _quiet_stdout)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints 'NCCL version ...' at init) may write to fd 1: keep fd 1 for the JSON line
+    only by pointing it at stderr for the rest of the run."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
     args = parse()
+    _quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -332,7 +350,7 @@ def main():
         cb = cpu_baseline(n, T, relax, rows=args.cpu_sample_rows)
         cb.pop("seconds_sample", None)
         line["cpu_baseline"] = cb
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
