@@ -108,15 +108,16 @@ def cpu_baseline(n, T, relax, rows=None, budget_s=20.0):
     cores = cpu_oracle.num_threads()
     rng = np.random.default_rng(1)
     if relax:
-        rows = rows or max(cores, min(T, 64))
+        rows = min(T, rows or T)  # default: the whole workload (~2 s wall on 16+ cores, ~40 core-seconds)
         X = rng.standard_normal((rows, n)).cumsum(0)
         t0 = time.perf_counter()
         cpu_oracle.mbd_counts_all(X)
         dt = time.perf_counter() - t0
         full = dt * T / rows  # MBD cost is linear in the number of rows
         return dict(value=n / full, unit="depth-evals/s", cores=cores, kind="port",
-                    sample="oracle/sd_oracle.c sdo_mbd_counts_all (qsort ranks per row) on %d of %d time rows x %d "
-                           "curves in %.2f s, scaled linearly to %d rows" % (rows, T, n, dt, T),
+                    sample="oracle/sd_oracle.c sdo_mbd_counts_all (qsort ranks per row, %d pthreads) on %d of %d time "
+                           "rows x %d curves in %.2f s%s" % (cores, rows, T, n, dt,
+                                                             "" if rows == T else ", scaled linearly to %d rows" % T),
                     seconds_sample=dt)
     X = rng.standard_normal((T, n)).cumsum(0)
     nq = max(cores, 16)
