@@ -24,8 +24,11 @@ constexpr int PAIR_TJ = PAIR_THREADS * PAIR_JPT;  // 1024 curves per J tile
 constexpr int PAIR_TK = 512;     // partner curves staged per K tile
 constexpr int PAIR_QCAP = 4096;
 
-// M[(q*W + w)*m + o] = {below bits, above bits} of other curve o vs query q over time points 32w..32w+31
-// (m = n - 1 others; curve id c = o + [o >= q]).
+// M[(q*W + w)*m + o] = {below bits, above bits} of other curve o vs query q (m = n - 1 others; curve id
+// c = o + [o >= q]).  Bit b of word w is time point t = w + W*b: every word SPANS the whole time axis, so
+// word 0 already samples 32 widely spaced time points.  (With 32 consecutive time points per word, sign
+// persistence of smooth curves let ~5 % of all pairs survive word 0 and the verification of survivors
+// dominated the kernel.)
 __global__ void __launch_bounds__(128) bd_mask_kernel(const double *__restrict__ X, const i64 T, const i64 n,
                                                       const i64 ld, const i64 *__restrict__ qidx, const int nqb,
                                                       const int W, uint2 *__restrict__ M,
@@ -37,7 +40,7 @@ __global__ void __launch_bounds__(128) bd_mask_kernel(const double *__restrict__
     if (threadIdx.x < MASK_QT) sqi[threadIdx.x] = q0 + threadIdx.x < nqb ? qidx[q0 + threadIdx.x] : 0;
     for (int i = threadIdx.x; i < 32 * MASK_QT; i += blockDim.x) {
         const int tt = i / MASK_QT, qq = i % MASK_QT;
-        const i64 t = (i64)w * 32 + tt;
+        const i64 t = (i64)w + (i64)W * tt;
         double v = 0.0;
         if (t < T && q0 + qq < nqb) v = X[t * ld + qidx[q0 + qq]];
         sq[tt][qq] = v;
@@ -54,9 +57,10 @@ __global__ void __launch_bounds__(128) bd_mask_kernel(const double *__restrict__
         shift[qq] = o >= sqi[qq];
     }
     bool bad = false;
-    const int tmax = (T - (i64)w * 32) < 32 ? (int)(T - (i64)w * 32) : 32;
-    for (int tt = 0; tt < tmax; ++tt) {
-        const double *row = X + ((i64)w * 32 + tt) * ld;
+    for (int tt = 0; tt < 32; ++tt) {
+        const i64 t = (i64)w + (i64)W * tt;
+        if (t >= T) break;
+        const double *row = X + t * ld;
         const double x0 = row[o], x1 = row[o + 1];  // o + 1 <= n - 1
         bad |= !isfinite(x0) || !isfinite(x1);
 #pragma unroll
