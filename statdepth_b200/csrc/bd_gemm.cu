@@ -32,7 +32,7 @@ constexpr int GM_KSTAGE = 2 * GM_TSTEP;             // K bytes per stage
 constexpr int GM_TILE_BYTES = GM_TILE * GM_KSTAGE;  // 16 KB
 constexpr int GM_STAGES = 3;                        // 3 x 32 KB of shared memory -> 2 CTAs per SM
 constexpr int GM_THREADS = 192;
-constexpr u32 GM_TMEM_COLS = 128;
+constexpr u32 GM_TMEM_COLS = 256;                   // two 128-column accumulators: MMA of tile i+1 overlaps epilogue of tile i
 constexpr u32 GM_CHUNK_PLANE = GM_TILE * 16;        // bytes of one k-chunk plane: 128 rows x 16 B = 2048
 
 // ---------------------------------------------------------------------------------------------
@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(GM_THREADS, 2) bd_gram_kernel(const uint8_t *_
     extern __shared__ __align__(1024) uint8_t gm_smem[];  // GM_STAGES x (A tile | B tile)
     __shared__ __align__(8) u64 full_bar[GM_STAGES];
     __shared__ __align__(8) u64 empty_bar[GM_STAGES];
-    __shared__ __align__(8) u64 tmem_full_bar;
-    __shared__ __align__(8) u64 tmem_empty_bar;
+    __shared__ __align__(8) u64 tmem_full_bar[2];
+    __shared__ __align__(8) u64 tmem_empty_bar[2];
     __shared__ u32 tmem_base_holder;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -191,8 +191,10 @@ __global__ void __launch_bounds__(GM_THREADS, 2) bd_gram_kernel(const uint8_t *_
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(&tmem_full_bar, 1);
-        mbar_init(&tmem_empty_bar, 4);  // one arrive per epilogue warp
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -232,8 +234,11 @@ __global__ void __launch_bounds__(GM_THREADS, 2) bd_gram_kernel(const uint8_t *_
             int stage = 0;
             u32 phase = 0, tile_it = 0;
             for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++tile_it) {
-                mbar_wait(&tmem_empty_bar, (tile_it & 1u) ^ 1u);  // epilogue has drained the accumulator
+                const u32 acc = tile_it & 1u;             // accumulator stage
+                const u32 use = (tile_it >> 1) & 1u;      // parity of this stage's use count
+                mbar_wait(&tmem_empty_bar[acc], use ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
+                const u32 tmem_d = tmem_base + acc * (u32)GM_TILE;
                 for (int ks = 0; ks < KS; ++ks) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -241,13 +246,13 @@ __global__ void __launch_bounds__(GM_THREADS, 2) bd_gram_kernel(const uint8_t *_
                     const u32 b0 = a0 + GM_TILE_BYTES;
 #pragma unroll
                     for (int k = 0; k < GM_KSTAGE / 32; ++k) {  // K = 32 bytes = 2 chunk planes per instruction
-                        tc_mma_i8(tmem_base, umma_desc(a0 + k * 2 * GM_CHUNK_PLANE),
+                        tc_mma_i8(tmem_d, umma_desc(a0 + k * 2 * GM_CHUNK_PLANE),
                                   umma_desc(b0 + k * 2 * GM_CHUNK_PLANE), GM_IDESC, (u32)((ks | k) != 0));
                     }
                     tc_commit(&empty_bar[stage]);  // smem stage is free once these MMAs have read it
                     if (++stage == GM_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(&tmem_full_bar);  // accumulator complete
+                tc_commit(&tmem_full_bar[acc]);  // accumulator complete
             }
         }
     } else {
@@ -259,24 +264,34 @@ __global__ void __launch_bounds__(GM_THREADS, 2) bd_gram_kernel(const uint8_t *_
         for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++tile_it) {
             int I, J;
             unrank_tile_pair(p, I, J);
-            mbar_wait(&tmem_full_bar, tile_it & 1u);
+            const u32 acc = tile_it & 1u, use = (tile_it >> 1) & 1u;
+            mbar_wait(&tmem_full_bar[acc], use);
             tc_fence_after();
             const int c1 = I * GM_TILE + row;
             const bool row_ok = c1 < n && c1 != qi;
+            // interior tiles (off the diagonal, fully inside n, not holding the query's column) only count zeros
+            const bool plain = I != J && (i64)(J + 1) * GM_TILE <= n && !(qi >= J * GM_TILE && qi < (J + 1) * GM_TILE);
+            u32 zeros = 0;
 #pragma unroll 1
             for (int cb = 0; cb < GM_TILE / 32; ++cb) {
                 u32 v[32];
-                tc_ld_32x32(tmem_base + ((u32)(quarter * 32) << 16) + (u32)(cb * 32), v);
-                const int c2base = J * GM_TILE + cb * 32;
+                tc_ld_32x32(tmem_base + ((u32)(quarter * 32) << 16) + acc * (u32)GM_TILE + (u32)(cb * 32), v);
+                if (plain) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int c2 = c2base + j;
-                    count += (u64)(row_ok && v[j] == 0u && c2 > c1 && c2 < n && c2 != qi);
+                    for (int j = 0; j < 32; ++j) zeros += (u32)(v[j] == 0u);
+                } else {
+                    const int c2base = J * GM_TILE + cb * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int c2 = c2base + j;
+                        zeros += (u32)(v[j] == 0u && c2 > c1 && c2 < n && c2 != qi);
+                    }
                 }
             }
+            if (row_ok) count += zeros;
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar);
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) count += __shfl_xor_sync(0xffffffffu, count, s);
