@@ -56,7 +56,7 @@ enum sd_layout {
 
 /* strict band-depth kernel selection (sd_set_option(ctx, SD_OPT_BD_IMPL, ...)) */
 enum sd_bd_impl {
-    SD_BD_AUTO = 0,
+    SD_BD_AUTO = 0, /* probe a few queries with the bit kernel; dense Gram if > 2 % of pairs survive word 0 */
     SD_BD_BITS = 1, /* bit-packed AND + early exit on CUDA cores                      */
     SD_BD_GEMM = 2  /* int8 violation Gram V = Sb Sb^T + Sa Sa^T on tcgen05 / TMEM    */
 };
@@ -93,6 +93,7 @@ typedef struct sd_timings {
     int64_t d2h_ns;      /* device->host copy of the result    */
     int64_t launches;    /* number of kernel launches          */
     int64_t fallback_rows; /* MBD: time rows ranked by the generic path (0 on well-spread data) */
+    int64_t bd_impl_used;  /* strict band depth: enum sd_bd_impl that did (most of) the work, 0 if n/a */
 } sd_timings;
 
 typedef struct sd_devinfo {

@@ -34,7 +34,7 @@ class EngineError(RuntimeError):
 
 class Timings(C.Structure):
     _fields_ = [("h2d_ns", C.c_int64), ("kernel_ns", C.c_int64), ("d2h_ns", C.c_int64),
-                ("launches", C.c_int64), ("fallback_rows", C.c_int64)]
+                ("launches", C.c_int64), ("fallback_rows", C.c_int64), ("bd_impl_used", C.c_int64)]
 
 
 class DevInfo(C.Structure):
@@ -146,7 +146,7 @@ class Engine:
         t = Timings()
         self._check(self.lib.sd_get_timings(self._ctx, C.byref(t)))
         return dict(h2d_ns=t.h2d_ns, kernel_ns=t.kernel_ns, d2h_ns=t.d2h_ns, launches=t.launches,
-                    fallback_rows=t.fallback_rows)
+                    fallback_rows=t.fallback_rows, bd_impl_used=t.bd_impl_used)
 
     def phase_ns(self) -> dict:
         """Per-phase device time of the last call (needs set_option(OPT_PROFILE, 1))."""

@@ -118,7 +118,7 @@ __device__ __forceinline__ void pair_drain(const PairQueue &pq, const uint2 *__r
 
 // grid (J tiles, queries).  CTA (jt, q): others o1 in J tile jt against every o2 > o1.
 __global__ void __launch_bounds__(PAIR_THREADS) bd_pair_kernel(const uint2 *__restrict__ M, const i64 m, const int W,
-                                                               i64 *__restrict__ out) {
+                                                               i64 *__restrict__ out, u64 *__restrict__ hits) {
     __shared__ uint2 s_tile[PAIR_TK];
     __shared__ uint2 s_queue[PAIR_QCAP];
     __shared__ int s_qn;
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) bd_pair_kernel(const uint2 *__re
     }
     if (threadIdx.x == 0) { s_qn = 0; s_total = 0ull; }
     u64 count = 0;
+    u32 nhit = 0;  // pairs that passed word 0 (statistics for SD_BD_AUTO)
     const i64 jend = j0 + PAIR_TJ < m ? j0 + PAIR_TJ : m;  // partners below jend may have o2 <= o1
     for (i64 k0 = j0; k0 < m; k0 += PAIR_TK) {
         __syncthreads();
@@ -155,7 +156,10 @@ __global__ void __launch_bounds__(PAIR_THREADS) bd_pair_kernel(const uint2 *__re
                 const int o2 = (int)(k0 + kk);
 #pragma unroll
                 for (int u = 0; u < PAIR_JPT; ++u)
-                    if (v[u] == 0u && ok1[u] && (!diag || o2 > o1[u])) pair_hit(pq, Mq, W, m, o1[u], o2, count);
+                    if (v[u] == 0u && ok1[u] && (!diag || o2 > o1[u])) {
+                        ++nhit;
+                        pair_hit(pq, Mq, W, m, o1[u], o2, count);
+                    }
             }
         }
         if (W > 1) {
@@ -171,6 +175,11 @@ __global__ void __launch_bounds__(PAIR_THREADS) bd_pair_kernel(const uint2 *__re
     if ((threadIdx.x & 31) == 0 && count) atomicAdd(&s_total, count);
     __syncthreads();
     if (threadIdx.x == 0 && s_total) atomicAdd((u64 *)&out[q], s_total);
+    if (hits) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) nhit += __shfl_xor_sync(0xffffffffu, nhit, s);
+        if ((threadIdx.x & 31) == 0 && nhit) atomicAdd(hits, (u64)nhit);
+    }
 }
 
 // J = 3, strict: triples (o1 < o2 < o3) of other curves never all-below / all-above.  O(n^3 W)
@@ -209,7 +218,7 @@ __global__ void iota_i64_kernel(i64 *p, i64 count) {
 
 // d_q == nullptr means all curves.  d_out[nq] receives the strict numerator for subset size j.
 int bd_strict_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq, int j,
-                     i64 *d_out) {
+                     i64 *d_out, u64 *d_hits) {
     if (n < 1 || T < 1 || ld < n || nq < 0) {
         set_error("strict band depth: bad shape T=%lld n=%lld ld=%lld nq=%lld", (long long)T, (long long)n,
                   (long long)ld, (long long)nq);
@@ -253,7 +262,7 @@ int bd_strict_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const 
         SD_TRY(prof_begin(ctx, SD_PHASE_BD_PAIRS));
         if (j == 2) {
             dim3 pgrid((unsigned)ceil_div(m, PAIR_TJ), (unsigned)nqb);
-            bd_pair_kernel<<<pgrid, PAIR_THREADS, 0, st>>>(M, m, (int)W, d_out + q0);
+            bd_pair_kernel<<<pgrid, PAIR_THREADS, 0, st>>>(M, m, (int)W, d_out + q0, d_hits);
         } else {
             const i64 npairs = m * (m - 1) / 2;
             dim3 tgrid((unsigned)ceil_div(npairs, 256), (unsigned)nqb);

@@ -91,7 +91,7 @@ struct sd_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // h2d start | kernels start | kernels end | d2h end
-    sd_timings last = {0, 0, 0, 0, 0};
+    sd_timings last = {0, 0, 0, 0, 0, 0};
     int bd_impl = SD_BD_AUTO;
     int mbd_force_fallback = 0;
     int profile = 0;
@@ -123,7 +123,7 @@ int band_depth_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const
 int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool want_j3, i64 *d_acc2,
                    i64 *d_acc3, int *d_rank_b, int *d_rank_a);
 int bd_strict_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq, int j,
-                     i64 *d_out);
+                     i64 *d_out, u64 *d_hits = nullptr);
 int bd_strict_gemm_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq,
                           i64 *d_out);
 int transpose_device(sd_ctx *ctx, const double *d_in, i64 rows, i64 cols, i64 ld_in, double *d_out);

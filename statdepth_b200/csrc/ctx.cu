@@ -43,7 +43,7 @@ void DevBuf::release() {
 
 int begin_call(sd_ctx *ctx) {
     SD_CUDA(cudaSetDevice(ctx->device));
-    ctx->last = sd_timings{0, 0, 0, 0, 0};
+    ctx->last = sd_timings{0, 0, 0, 0, 0, 0};
     ctx->prof_n = 0;
     for (int i = 0; i < SD_PHASE_COUNT; ++i) ctx->phase_ns[i] = 0;
     SD_CUDA(cudaMemsetAsync(ctx->d_status, 0, 4 * sizeof(int), ctx->stream));

@@ -177,6 +177,22 @@ def test_strict_tcgen05_gram_bit_exact(engine, oracle, T, n, seed, maker):
         engine.set_option(E.OPT_BD_IMPL, E.BD_AUTO)
 
 
+def test_strict_auto_selects_by_survivor_rate(engine, oracle):
+    """SD_BD_AUTO probes 8 queries with the bit kernel: crossing curves stay on it, non-crossing curves
+    (about half of all pairs survive every mask word) switch to the data-independent tcgen05 Gram."""
+    from statdepth_b200 import _engine as E
+    rng = np.random.default_rng(23)
+    T, n = 96, 1300
+    q = np.arange(0, n, 13)  # 100 queries
+    X = rng.standard_normal((T, n)).cumsum(0)
+    assert (engine.band_depth_counts(X, q, 2, False) == oracle.bd_counts(X, q)).all()
+    assert engine.timings()["bd_impl_used"] == E.BD_BITS
+    Xn = np.outer(rng.random(T) + 0.1, rng.random(n))
+    assert (engine.band_depth_counts(Xn, q, 2, False) == oracle.bd_counts(Xn, q)).all()
+    assert engine.timings()["bd_impl_used"] == E.BD_GEMM
+    assert (engine.band_depth_counts(Xn, None, 2, False)[q] == oracle.bd_counts(Xn, q)).all()
+
+
 def test_strict_j3(engine, oracle):
     X = walks(61, 40, 60)
     assert (engine.band_depth_counts(X, None, 3, False) == oracle.bd_counts(X, j=3)).all()
