@@ -7,20 +7,23 @@
 // so the whole relaxed numerator is a per-row ranking problem (kernel "K1").
 //
 // Pipeline per block of time rows (all kernels on ctx->stream, no host sync):
-//   1. mbd_splitters_kernel : one CTA per row sorts a strided sample in shared memory (bitonic)
-//                             and emits P-1 equal-mass splitter VALUES.
-//   2. mbd_partition_kernel : streams the row once from HBM, binary-searches the splitters and
-//                             appends (value, curve id) to the part's slot list (fixed capacity CAP,
-//                             one global atomic per element).  Equal values always share a part, so
-//                             tie runs never straddle parts.
-//   3. mbd_rank_kernel      : ONE WARP per (row, part): loads <= CAP values, maps them to a 22-bit
+//   1. mbd_splitters_kernel : one CTA per row sorts a strided sample (u32 images of float(x - x[0]), register
+//                             bitonic network per warp + swizzled shared-memory merges) and emits P-1
+//                             equal-mass splitters.
+//   2. mbd_partition_kernel : streams the row once from HBM, finds each value's part with a bucket table,
+//                             groups a 4096-value chunk by part in shared memory (one shared atomic per
+//                             value, one global atomic per (CTA, part)) and copies the groups to the parts'
+//                             slot lists (fixed capacity CAP) with coalesced stores.  Equal values always
+//                             share a part, so tie runs never straddle parts.
+//   3. mbd_rank_kernel      : ONE WARP per (row, part): loads <= 512 values, maps them to a 22-bit
 //                             monotone key packed with the slot id, sorts the packed u32 keys in
 //                             registers with a shuffle bitonic network, resolves equal-key runs with
 //                             exact fp64 compares, and adds term(b, a) to acc[curve] with a 64-bit RED.
+//      mbd_rank_big_kernel  : persistent; drains the work list of parts with 513..1024 values.
 //   4. mbd_fallback_kernel  : rows in which some part overflowed CAP (heavy ties, adversarial
 //                             distributions) are ranked by a generic one-CTA-per-row bitonic sort of
 //                             order-preserving u64 keys + binary-search ranks.  Correct for any
-//                             finite input; ~3x slower.
+//                             finite input; slower.
 // HBM layout: X[t*ld + c] float64 (time-major rows are contiguous and streamed with coalesced
 // loads); acc int64[n]; part lists [row][part][CAP] float64 + uint32.
 #include <stdlib.h>
