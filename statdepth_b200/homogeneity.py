@@ -169,13 +169,58 @@ def P2_homogeneity(F: pd.DataFrame, G: pd.DataFrame, K=None, J=2, containment='r
     return np.abs(P1_F_G - P1_F_F)
 
 
+def _perm_stats_batched(pooled: pd.DataFrame, nF: int, perms: np.ndarray, method: str, relax: bool) -> np.ndarray:
+    """p1 / p2 statistics of all permutations with two or three BATCHED engine calls
+    (sd_band_depth_batched_f64: one launch sequence for all permutations) instead of 2-3 calls per
+    permutation.  Same arithmetic and the same tie-breaking (pandas sort) as FunctionalHomogeneity."""
+    from scipy.special import binom
+
+    from ._engine import get_engine
+    eng = get_engine()
+    X = np.ascontiguousarray(pooled.to_numpy(dtype=np.float64))
+    T, n = X.shape
+    B = perms.shape[0]
+    nG = n - nF
+
+    def depths(membership, queries, sizes):
+        cnt = eng.band_depth_counts_batched(X, membership, queries, 2, relax).astype(np.float64)
+        if relax:
+            cnt = cnt / float(T)
+        return cnt / binom(sizes, 2)[:, None]
+
+    # (1) depth of every curve of G_b inside G_b  -> deepest curve of G_b
+    memG = np.zeros((B, n), dtype=np.uint8)
+    for b in range(B):
+        memG[b, perms[b, nF:]] = 1
+    qG = np.ascontiguousarray(perms[:, nF:])
+    dG = depths(memG, qG, np.full(B, nG))
+    deepest = np.empty(B, dtype=np.int64)
+    for b in range(B):
+        deepest[b] = pd.Series(index=qG[b], data=dG[b]).sort_values(ascending=False).index[0]
+    # (2) depth of that curve inside F_b u {g}
+    memF = np.zeros((B, n), dtype=np.uint8)
+    for b in range(B):
+        memF[b, perms[b, :nF]] = 1
+        memF[b, deepest[b]] = 1
+    g_in_F = depths(memF, deepest[:, None], np.full(B, nF + 1))[:, 0]
+    if method == 'p1':
+        return g_in_F
+    # (3) p2: | depth(g in F u {g}) - max depth of F_b in F_b |
+    memF0 = np.zeros((B, n), dtype=np.uint8)
+    for b in range(B):
+        memF0[b, perms[b, :nF]] = 1
+    dF = depths(memF0, np.ascontiguousarray(perms[:, :nF]), np.full(B, nF))
+    return np.abs(g_in_F - dF.max(axis=1))
+
+
 def permutation_test(F: pd.DataFrame, G: pd.DataFrame, method='p1', B=200, seed=None, J=2, containment='r2',
-                     relax=True) -> dict:
+                     relax=True, batched=True) -> dict:
     """Permutation null of a functional homogeneity coefficient (NEW: no reference counterpart).
 
     The observed statistic is FunctionalHomogeneity([F], [G], method); the null re-labels the pooled
     curves B times with np.random.default_rng(seed).permutation and re-evaluates it.  Permutations are
-    independent: with torch.distributed initialised they are split across ranks and all-gathered.
+    independent: with torch.distributed initialised they are split across ranks and all-gathered; within a
+    rank p1 / p2 are evaluated for all permutations by batched engine calls (`batched=False` loops instead).
     Returns dict(observed, null (B floats), p_value = P(null more extreme than observed)).
     """
     from . import _dist
@@ -193,6 +238,9 @@ def permutation_test(F: pd.DataFrame, G: pd.DataFrame, method='p1', B=200, seed=
     observed = stat(pooled.iloc[:, :nF], pooled.iloc[:, nF:])
 
     def run(block):
+        block = list(block)
+        if batched and method in ('p1', 'p2') and J == 2 and containment == 'r2' and block:
+            return _perm_stats_batched(pooled, nF, perms[block], method, relax)
         return np.array([stat(pooled.iloc[:, perms[b][:nF]], pooled.iloc[:, perms[b][nF:]]) for b in block])
 
     # the inner depth calls must not shard again while permutations are sharded across ranks

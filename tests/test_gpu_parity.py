@@ -415,3 +415,9 @@ def test_homogeneity_and_permutation_test(golden):
     out = permutation_test(F, G, method='p1', B=20, seed=5)
     assert out["null"].shape == (20,) and 0.0 < out["p_value"] <= 1.0
     assert out["p_value"] < 0.2  # a 6-sigma shift is not exchangeable
+    loop = permutation_test(F, G, method='p1', B=20, seed=5, batched=False)
+    assert loop["null"].tolist() == out["null"].tolist() and loop["observed"] == out["observed"]
+    for method in ("p2",):
+        a = permutation_test(F, G, method=method, B=10, seed=6, relax=False)
+        b = permutation_test(F, G, method=method, B=10, seed=6, relax=False, batched=False)
+        assert a["null"].tolist() == b["null"].tolist()

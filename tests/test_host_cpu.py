@@ -134,3 +134,20 @@ def test_j4_relaxed_from_ranks(host_on_oracle, oracle):
     np.testing.assert_allclose(res.values, exp, rtol=1e-13)
     with pytest.raises(NotImplementedError):
         FunctionalDepth([pd.DataFrame(X)], J=4, relax=False)
+
+
+def test_permutation_test_batched_equals_loop(host_on_oracle, monkeypatch):
+    """permutation_test: the batched evaluation (2-3 engine calls for all permutations) reproduces the
+    per-permutation FunctionalHomogeneity loop exactly, including tie-breaking of the deepest curve."""
+    import statdepth_b200._engine as eng_mod
+    from statdepth_b200.homogeneity import permutation_test
+    monkeypatch.setattr(eng_mod, "get_engine", lambda device=None: host_on_oracle)
+    rng = np.random.default_rng(5)
+    F = pd.DataFrame(rng.standard_normal((12, 9)).cumsum(0))
+    G = pd.DataFrame(np.round(rng.standard_normal((12, 8)).cumsum(0)) + 1.0)  # ties included
+    for method in ("p1", "p2"):
+        for relax in (True, False):
+            a = permutation_test(F, G, method=method, B=12, seed=3, relax=relax, batched=True)
+            b = permutation_test(F, G, method=method, B=12, seed=3, relax=relax, batched=False)
+            assert a["observed"] == b["observed"] and a["p_value"] == b["p_value"]
+            assert a["null"].tolist() == b["null"].tolist()
