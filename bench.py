@@ -313,11 +313,17 @@ def main():
     peak, peak_src = peaks()
     # roofline of the rank pipeline (all kernels of a step): algorithmic bytes = 8*n*T_local read once + 8*n written
     alg_bytes = 8.0 * n * Tl + 8.0 * n
+    alg_bytes_placeholder = alg_bytes
     kern_s = kern_ns / 1e9 / args.steps
     achieved = alg_bytes / kern_s / 1e9
     dominant = max(phases, key=phases.get) if phases else None
+    # DRAM traffic of one step: ncu --set full (profiles/ncu_r01_final_summary.md) measured 405 MB for a
+    # 128-row block of 100k curves (sample read + one HBM round trip of the part lists) = 3.95 bytes per
+    # algorithmic byte; scaled to this rank's rows.  null for other shapes.
+    traffic = 3.95 * alg_bytes_placeholder if n == 100_000 else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": traffic, "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, round-1 capture, scaled by rows",
+            "peak_source": peak_src,
             "kernel": "all kernels of one step (per-rank); dominant phase: %s" % dominant,
             "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": kern_s * 1e3,
             "phase_ms_per_step": {k: v / 1e6 / args.steps for k, v in phases.items()}}

@@ -90,6 +90,8 @@ struct sd_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                         // H2D of row blocks overlapped with ranking
+    cudaEvent_t ev_pipe[4] = {nullptr, nullptr, nullptr, nullptr};  // copied[2], consumed[2]
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // h2d start | kernels start | kernels end | d2h end
     sd_timings last = {0, 0, 0, 0, 0, 0};
     int bd_impl = SD_BD_AUTO;
@@ -121,7 +123,7 @@ int prof_end(sd_ctx *ctx);
 int band_depth_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq, int j,
                       int relax, i64 *d_out);
 int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool want_j3, i64 *d_acc2,
-                   i64 *d_acc3, int *d_rank_b, int *d_rank_a);
+                   i64 *d_acc3, int *d_rank_b, int *d_rank_a, bool accumulate = false);
 int bd_strict_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq, int j,
                      i64 *d_out, u64 *d_hits = nullptr);
 int bd_strict_gemm_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq,

@@ -214,6 +214,8 @@ int sd_init(int device, sd_ctx **out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     SD_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    SD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) SD_CUDA(cudaEventCreateWithFlags(&ctx->ev_pipe[i], cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) SD_CUDA(cudaEventCreate(&ctx->ev[i]));
     SD_CUDA(cudaMalloc(&ctx->d_status, 4 * sizeof(int)));
     SD_CUDA(cudaMallocHost(&ctx->h_status, 4 * sizeof(int)));
@@ -233,6 +235,9 @@ int sd_destroy(sd_ctx *ctx) {
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2 * sd_ctx::MAX_PROF; ++i)
         if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->ev_pipe[i]) cudaEventDestroy(ctx->ev_pipe[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SD_OK;

@@ -702,9 +702,9 @@ static int pow2ceil_int(i64 v) {
 }
 
 // Sum over ALL curves of one matrix: d_acc2[c] (and d_acc3[c]) += sum_t term_j(b,a).  The
-// accumulators are zeroed here.  Optional per-(t,c) rank output.
+// accumulators are zeroed here unless `accumulate` (row blocks of one matrix).  Optional per-(t,c) rank output.
 int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool want_j3, i64 *d_acc2, i64 *d_acc3,
-                   int *d_rank_b, int *d_rank_a) {
+                   int *d_rank_b, int *d_rank_a, bool accumulate) {
     if (n < 1 || T < 0 || ld < n) {
         set_error("mbd: bad shape T=%lld n=%lld ld=%lld", (long long)T, (long long)n, (long long)ld);
         return SD_ERR_INVALID;
@@ -714,8 +714,10 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         return SD_ERR_UNSUPPORTED;
     }
     cudaStream_t st = ctx->stream;
-    SD_CUDA(cudaMemsetAsync(d_acc2, 0, (size_t)n * sizeof(i64), st));
-    if (want_j3) SD_CUDA(cudaMemsetAsync(d_acc3, 0, (size_t)n * sizeof(i64), st));
+    if (!accumulate) {
+        SD_CUDA(cudaMemsetAsync(d_acc2, 0, (size_t)n * sizeof(i64), st));
+        if (want_j3) SD_CUDA(cudaMemsetAsync(d_acc3, 0, (size_t)n * sizeof(i64), st));
+    }
     if (T == 0) return SD_OK;
 
     int target = TARGET_PART;

@@ -98,6 +98,22 @@ def test_layouts_queries_and_ld(engine, oracle):
     assert (out == ref).all()
 
 
+def test_pipelined_host_path(engine, oracle):
+    """Inputs >= 64 MB take the row-block pipeline (H2D of block k+1 overlaps ranking of block k); also
+    with a padded leading dimension and with J = 3."""
+    T, n, ld = 70, 150_000, 150_016
+    wide = np.zeros((T, ld))
+    wide[:, :n] = walks(43, T, n)
+    X = np.ascontiguousarray(wide[:, :n])
+    exp = oracle.mbd_counts_all(X)
+    assert (engine.band_depth_counts(X, None, 2, True) == exp).all()
+    assert engine.timings()["launches"] > 12  # several row blocks
+    q = np.array([149_999, 3, 77_777])
+    out = engine.band_depth_counts_ptr(wide.ctypes.data, T, n, ld, q, 2, True)
+    assert (out == exp[q]).all()
+    assert (engine.band_depth_counts(X, q, 3, True) == oracle.mbd_counts_all(X, j=3)[q]).all()
+
+
 def test_nonfinite_is_rejected(engine):
     from statdepth_b200 import EngineError
     X = walks(51, 8, 1200)
