@@ -38,45 +38,59 @@ constexpr u32 GM_CHUNK_PLANE = GM_TILE * 16;        // bytes of one k-chunk plan
 // ---------------------------------------------------------------------------------------------
 // operand generation
 // ---------------------------------------------------------------------------------------------
-// grid (row blocks, k stages, queries of the batch), 128 threads = 128 rows
+// grid (row blocks, 2 * k stages, ceil(queries / GM_MQ)), 128 threads = 128 rows.  One CTA builds half a
+// stage (32 time points -> 2 "below" + 2 "above" 16-byte chunks per row) for GM_MQ queries, so X is read
+// once per GM_MQ queries.
+constexpr int GM_MQ = 4;
+
 __global__ void __launch_bounds__(GM_TILE) bd_mask8_kernel(const double *__restrict__ X, const i64 T, const i64 n,
-                                                           const i64 ld, const i64 *__restrict__ qidx, const int NB,
-                                                           const int KS, uint8_t *__restrict__ M8,
+                                                           const i64 ld, const i64 *__restrict__ qidx, const int nqb,
+                                                           const int NB, const int KS, uint8_t *__restrict__ M8,
                                                            int *__restrict__ status) {
-    __shared__ double sq[GM_TSTEP];
-    const int rb = blockIdx.x, ks = blockIdx.y, q = blockIdx.z;
-    const i64 qi = qidx[q];
-    const i64 t0 = (i64)ks * GM_TSTEP;
-    if (threadIdx.x < GM_TSTEP) {
-        const i64 t = t0 + threadIdx.x;
-        sq[threadIdx.x] = t < T ? X[t * ld + qi] : 0.0;
+    __shared__ double sq[32][GM_MQ];
+    const int rb = blockIdx.x, ks = blockIdx.y >> 1, half = blockIdx.y & 1, q0 = blockIdx.z * GM_MQ;
+    const i64 t0 = (i64)ks * GM_TSTEP + half * 32;
+    {
+        const int tt = threadIdx.x / GM_MQ, qq = threadIdx.x % GM_MQ;  // 128 threads = 32 x 4
+        const i64 t = t0 + tt;
+        sq[tt][qq] = (t < T && q0 + qq < nqb) ? X[t * ld + qidx[q0 + qq]] : 0.0;
     }
     __syncthreads();
     const i64 c = (i64)rb * GM_TILE + threadIdx.x;
-    u32 below[16], above[16];  // 64 bytes each, 4 bytes per word
+    u32 below[GM_MQ][8], above[GM_MQ][8];  // 32 bytes each per query
 #pragma unroll
-    for (int w = 0; w < 16; ++w) below[w] = above[w] = 0u;
+    for (int qq = 0; qq < GM_MQ; ++qq)
+#pragma unroll
+        for (int w = 0; w < 8; ++w) below[qq][w] = above[qq][w] = 0u;
     bool bad = false;
     if (c < n) {
 #pragma unroll
-        for (int tt = 0; tt < GM_TSTEP; ++tt) {
+        for (int tt = 0; tt < 32; ++tt) {
             const i64 t = t0 + tt;
             if (t < T) {
-                const double x = X[t * ld + c], xq = sq[tt];
+                const double x = X[t * ld + c];
                 bad |= !isfinite(x);
-                below[tt >> 2] |= (u32)(x < xq) << ((tt & 3) * 8);
-                above[tt >> 2] |= (u32)(x > xq) << ((tt & 3) * 8);
+#pragma unroll
+                for (int qq = 0; qq < GM_MQ; ++qq) {
+                    const double xq = sq[tt][qq];
+                    below[qq][tt >> 2] |= (u32)(x < xq) << ((tt & 3) * 8);
+                    above[qq][tt >> 2] |= (u32)(x > xq) << ((tt & 3) * 8);
+                }
             }
         }
     }
     if (bad) atomicOr(status, ST_NONFINITE);
-    uint8_t *tile = M8 + (((i64)q * NB + rb) * KS + ks) * GM_TILE_BYTES;
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-        *reinterpret_cast<uint4 *>(tile + (size_t)ch * GM_CHUNK_PLANE + threadIdx.x * 16) =
-            make_uint4(below[4 * ch], below[4 * ch + 1], below[4 * ch + 2], below[4 * ch + 3]);
-        *reinterpret_cast<uint4 *>(tile + (size_t)(4 + ch) * GM_CHUNK_PLANE + threadIdx.x * 16) =
-            make_uint4(above[4 * ch], above[4 * ch + 1], above[4 * ch + 2], above[4 * ch + 3]);
+    for (int qq = 0; qq < GM_MQ; ++qq) {
+        if (q0 + qq >= nqb) break;
+        uint8_t *tile = M8 + (((i64)(q0 + qq) * NB + rb) * KS + ks) * GM_TILE_BYTES;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            *reinterpret_cast<uint4 *>(tile + (size_t)(2 * half + ch) * GM_CHUNK_PLANE + threadIdx.x * 16) =
+                make_uint4(below[qq][4 * ch], below[qq][4 * ch + 1], below[qq][4 * ch + 2], below[qq][4 * ch + 3]);
+            *reinterpret_cast<uint4 *>(tile + (size_t)(4 + 2 * half + ch) * GM_CHUNK_PLANE + threadIdx.x * 16) =
+                make_uint4(above[qq][4 * ch], above[qq][4 * ch + 1], above[qq][4 * ch + 2], above[qq][4 * ch + 3]);
+        }
     }
 }
 
@@ -333,7 +347,7 @@ int bd_strict_gemm_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, c
     }
     const int NB = (int)ceil_div(n, GM_TILE);
     const int KS = (int)ceil_div(T, GM_TSTEP);
-    if (KS > 65535) {
+    if (2 * KS > 65535) {
         set_error("strict band depth (gemm): T too large");
         return SD_ERR_UNSUPPORTED;
     }
@@ -351,8 +365,8 @@ int bd_strict_gemm_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, c
     for (i64 q0 = 0; q0 < nq; q0 += QB) {
         const int nqb = (int)(nq - q0 < QB ? nq - q0 : QB);
         SD_TRY(prof_begin(ctx, SD_PHASE_BD_MASKS));
-        bd_mask8_kernel<<<dim3((unsigned)NB, (unsigned)KS, (unsigned)nqb), GM_TILE, 0, st>>>(dX, T, n, ld, d_q + q0, NB,
-                                                                                         KS, M8, ctx->d_status);
+        bd_mask8_kernel<<<dim3((unsigned)NB, (unsigned)(2 * KS), (unsigned)ceil_div(nqb, GM_MQ)), GM_TILE, 0, st>>>(
+            dX, T, n, ld, d_q + q0, nqb, NB, KS, M8, ctx->d_status);
         SD_TRY(prof_end(ctx));
         ctx->last.launches++;
         SD_TRY(prof_begin(ctx, SD_PHASE_BD_PAIRS));
