@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--T", type=int, default=None)
     ap.add_argument("--cpu-sample-rows", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--bd-impl", default="auto", choices=["auto", "bits", "gemm"])
+    ap.add_argument("--bd-impl", default="auto", choices=["auto", "bits", "gemm", "match"])
     ap.add_argument("--nq", type=int, default=None, help="bd workload: number of query curves (default all)")
     return ap.parse_args()
 
@@ -197,7 +197,7 @@ def main():
     relax = args.workload == "mbd"
     eng = E.Engine(local)
     eng.set_option(E.OPT_PROFILE, 1)
-    eng.set_option(E.OPT_BD_IMPL, {"auto": E.BD_AUTO, "bits": E.BD_BITS, "gemm": E.BD_GEMM}[args.bd_impl])
+    eng.set_option(E.OPT_BD_IMPL, {"auto": E.BD_AUTO, "bits": E.BD_BITS, "gemm": E.BD_GEMM, "match": E.BD_MATCH}[args.bd_impl])
     dev = torch.device("cuda", local)
 
     # ---- synthetic input: float64 random walks (they cross), identical on every rank ---------------

@@ -56,9 +56,12 @@ enum sd_layout {
 
 /* strict band-depth kernel selection (sd_set_option(ctx, SD_OPT_BD_IMPL, ...)) */
 enum sd_bd_impl {
-    SD_BD_AUTO = 0, /* probe a few queries with the bit kernel; dense Gram if > 2 % of pairs survive word 0 */
-    SD_BD_BITS = 1, /* bit-packed AND + early exit on CUDA cores                      */
-    SD_BD_GEMM = 2  /* int8 violation Gram V = Sb Sb^T + Sa Sa^T on tcgen05 / TMEM    */
+    SD_BD_AUTO = 0,  /* sign-vector matching when it applies; queries it cannot certify (ties with the query,
+                        n > 8193) go to the bit kernel, or to the dense Gram if a probe of 8 queries shows that
+                        more than 2 % of all pairs survive the first mask word */
+    SD_BD_BITS = 1,  /* bit-packed AND + early exit on CUDA cores                      */
+    SD_BD_GEMM = 2,  /* int8 violation Gram V = Sb Sb^T + Sa Sa^T on tcgen05 / TMEM    */
+    SD_BD_MATCH = 3  /* complementary sign-vector matching (O(nT) per query) + enumeration of uncertified queries */
 };
 
 enum sd_option {

@@ -16,7 +16,7 @@ SD_OK = 0
 STATUS_NAMES = {1: "SD_ERR_INVALID", 2: "SD_ERR_CUDA", 3: "SD_ERR_NO_DEVICE", 4: "SD_ERR_NONFINITE",
                 5: "SD_ERR_OVERFLOW", 6: "SD_ERR_UNSUPPORTED"}
 LAYOUT_TN, LAYOUT_NT = 0, 1
-BD_AUTO, BD_BITS, BD_GEMM = 0, 1, 2
+BD_AUTO, BD_BITS, BD_GEMM, BD_MATCH = 0, 1, 2, 3
 OPT_BD_IMPL, OPT_MBD_FORCE_FALLBACK, OPT_PROFILE, OPT_SIMPLICIAL_IMPL = 1, 2, 3, 4
 SIMPLICIAL_AUTO, SIMPLICIAL_ENUMERATE, SIMPLICIAL_COUNT = 0, 1, 2
 PHASES = ("mbd_splitters", "mbd_partition", "mbd_rank", "mbd_generic", "bd_masks", "bd_pairs", "p6", "p7")

@@ -26,6 +26,7 @@ SOURCES = {
     "mbd.cu": [],
     "bd_bits.cu": [],
     "bd_gemm.cu": [],
+    "bd_match.cu": [],
     "pointcloud.cu": ["-fmad=false"],
     "simplicial_count.cu": ["-fmad=false"],
 }

@@ -6,6 +6,43 @@
 
 namespace sd {
 
+// strict J = 2 by enumeration: bit kernel, or the dense Gram when a probe of 8 queries shows that the bit
+// kernel would drown in survivors (non-crossing / tie-heavy curves)
+static int strict_enumerate(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq, i64 *d_out) {
+    if (ctx->bd_impl == SD_BD_GEMM) {
+        ctx->last.bd_impl_used = SD_BD_GEMM;
+        return bd_strict_gemm_device(ctx, dX, T, n, ld, d_q, nq, d_out);
+    }
+    if (ctx->last.bd_impl_used == 0) ctx->last.bd_impl_used = SD_BD_BITS;
+    constexpr i64 PROBE = 8;
+    if (ctx->bd_impl == SD_BD_BITS || nq <= 4 * PROBE || n < 1024)
+        return bd_strict_device(ctx, dX, T, n, ld, d_q, nq, 2, d_out);
+    SD_TRY(ctx->buf[BUF_WORK].reserve(sizeof(u64)));
+    u64 *d_hits = ctx->buf[BUF_WORK].as<u64>();
+    SD_CUDA(cudaMemsetAsync(d_hits, 0, sizeof(u64), ctx->stream));
+    i64 *iq = nullptr;
+    if (!d_q) {  // materialise the identity so that the probe and the remainder can be offset
+        SD_TRY(ctx->buf[BUF_QIDX].reserve((size_t)nq * sizeof(i64) * 2));
+        iq = ctx->buf[BUF_QIDX].as<i64>() + nq;
+        std::vector<i64> h((size_t)nq);
+        for (i64 i = 0; i < nq; ++i) h[(size_t)i] = i;
+        SD_CUDA(cudaMemcpyAsync(iq, h.data(), (size_t)nq * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
+        SD_CUDA(cudaStreamSynchronize(ctx->stream));
+        d_q = iq;
+    }
+    SD_TRY(bd_strict_device(ctx, dX, T, n, ld, d_q, PROBE, 2, d_out, d_hits));
+    u64 h_hits = 0;
+    SD_CUDA(cudaMemcpyAsync(&h_hits, d_hits, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double pairs = (double)PROBE * 0.5 * (double)(n - 1) * (double)(n - 2);
+    if ((double)h_hits > 0.02 * pairs) {
+        ctx->last.bd_impl_used = SD_BD_GEMM;
+        return bd_strict_gemm_device(ctx, dX, T, n, ld, d_q + PROBE, nq - PROBE, d_out + PROBE);
+    }
+    ctx->last.bd_impl_used = SD_BD_BITS;
+    return bd_strict_device(ctx, dX, T, n, ld, d_q + PROBE, nq - PROBE, 2, d_out + PROBE);
+}
+
 // dispatch one subset size j on device-resident data
 int band_depth_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq, int j,
                       int relax, i64 *d_out) {
@@ -14,40 +51,17 @@ int band_depth_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const
         return SD_ERR_UNSUPPORTED;
     }
     if (!relax) {
-        if (j == 2 && ctx->bd_impl == SD_BD_GEMM) {
-            ctx->last.bd_impl_used = SD_BD_GEMM;
-            return bd_strict_gemm_device(ctx, dX, T, n, ld, d_q, nq, d_out);
+        if (j == 3) {
+            ctx->last.bd_impl_used = SD_BD_BITS;
+            return bd_strict_device(ctx, dX, T, n, ld, d_q, nq, 3, d_out);
         }
-        ctx->last.bd_impl_used = SD_BD_BITS;
-        constexpr i64 PROBE = 8;
-        if (j != 2 || ctx->bd_impl == SD_BD_BITS || nq <= 4 * PROBE || n < 1024)
-            return bd_strict_device(ctx, dX, T, n, ld, d_q, nq, j, d_out);
-        // SD_BD_AUTO: the bit kernel's cost grows with the number of pairs that survive the first mask
-        // word (non-crossing / tie-heavy curves: up to half of all pairs), the dense Gram's does not.
-        // Probe a few queries, then choose for the rest.
-        SD_TRY(ctx->buf[BUF_WORK].reserve(sizeof(u64)));
-        u64 *d_hits = ctx->buf[BUF_WORK].as<u64>();
-        SD_CUDA(cudaMemsetAsync(d_hits, 0, sizeof(u64), ctx->stream));
-        i64 *iq = nullptr;
-        if (!d_q) {  // materialise the identity so that the probe and the remainder can be offset
-            SD_TRY(ctx->buf[BUF_QIDX].reserve((size_t)nq * sizeof(i64) * 2));
-            iq = ctx->buf[BUF_QIDX].as<i64>() + nq;
-            std::vector<i64> h((size_t)nq);
-            for (i64 i = 0; i < nq; ++i) h[(size_t)i] = i;
-            SD_CUDA(cudaMemcpyAsync(iq, h.data(), (size_t)nq * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
-            SD_CUDA(cudaStreamSynchronize(ctx->stream));
-            d_q = iq;
-        }
-        SD_TRY(bd_strict_device(ctx, dX, T, n, ld, d_q, PROBE, 2, d_out, d_hits));
-        u64 h_hits = 0;
-        SD_CUDA(cudaMemcpyAsync(&h_hits, d_hits, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-        SD_CUDA(cudaStreamSynchronize(ctx->stream));
-        const double pairs = (double)PROBE * 0.5 * (double)(n - 1) * (double)(n - 2);
-        if ((double)h_hits > 0.02 * pairs) {
-            ctx->last.bd_impl_used = SD_BD_GEMM;
-            return bd_strict_gemm_device(ctx, dX, T, n, ld, d_q + PROBE, nq - PROBE, d_out + PROBE);
-        }
-        return bd_strict_device(ctx, dX, T, n, ld, d_q + PROBE, nq - PROBE, 2, d_out + PROBE);
+        ctx->last.bd_impl_used = 0;
+        const bool match = (ctx->bd_impl == SD_BD_MATCH || ctx->bd_impl == SD_BD_AUTO) && bd_match_supported(T, n);
+        if (!match) return strict_enumerate(ctx, dX, T, n, ld, d_q, nq, d_out);
+        i64 nfb = 0;
+        SD_TRY(bd_strict_match_device(ctx, dX, T, n, ld, d_q, nq, d_out, strict_enumerate, &nfb));
+        if (2 * nfb <= nq) ctx->last.bd_impl_used = SD_BD_MATCH;  // else: what strict_enumerate chose
+        return SD_OK;
     }
     // overflow guard: T * C(n-1, j) must fit in int64
     {

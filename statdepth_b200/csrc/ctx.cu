@@ -267,7 +267,7 @@ int sd_set_option(sd_ctx *ctx, int option, int64_t value) {
     }
     switch (option) {
         case SD_OPT_BD_IMPL:
-            if (value < SD_BD_AUTO || value > SD_BD_GEMM) {
+            if (value < SD_BD_AUTO || value > SD_BD_MATCH) {
                 sd::set_error("sd_set_option: bad SD_OPT_BD_IMPL value %lld", (long long)value);
                 return SD_ERR_INVALID;
             }

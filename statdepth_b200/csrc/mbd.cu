@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "sortnet.cuh"
 
 namespace sd {
 
@@ -45,79 +46,6 @@ __device__ __forceinline__ i64 comb2_dev(i64 m) { return m * (m - 1) / 2; }
 __device__ __forceinline__ i64 comb3_dev(i64 m) {
     // m(m-1)/2 is exact; (m(m-1)/2)*(m-2) is divisible by 3; fits in int64 for m < 2.6e6
     return m < 3 ? 0 : (m * (m - 1) / 2) * (m - 2) / 3;
-}
-
-__device__ __forceinline__ void ce_u32(u32 &a, u32 &b) {
-    const u32 lo = min(a, b), hi = max(a, b);
-    a = lo;
-    b = hi;
-}
-
-// Register-resident bitonic network over 32*EPL keys held as v[i] at element index e = lane*EPL + i,
-// in its "always ascending" form: the first stage of every merge pairs e with its mirror e ^ (k-1), the
-// remaining stages pair e with e ^ j, and every compare-exchange puts the minimum at the lower index.
-// Stages inside a lane are unrolled on registers; stages across lanes are ROLLED loops over the lane
-// mask -- the fully unrolled network was ~35k SASS instructions and the rank kernel spent 70% of its
-// stall samples in stall_no_inst (profiles/ncu_mbd_r01a_summary.md): code size matters more than loop
-// overhead here.
-template <int EPL>
-__device__ __forceinline__ void lane_tail(u32 (&v)[EPL]) {  // xor stages j = EPL/2 .. 1
-#pragma unroll
-    for (int j = EPL >> 1; j > 0; j >>= 1) {
-#pragma unroll
-        for (int i = 0; i < EPL; ++i)
-            if ((i & j) == 0) ce_u32(v[i], v[i | j]);
-    }
-}
-
-template <int EPL>
-__device__ __forceinline__ void lane_sort(u32 (&v)[EPL]) {  // every lane sorts its own EPL keys
-#pragma unroll
-    for (int k = 2; k <= EPL; k <<= 1) {
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-            const int p = i ^ (k - 1);
-            if (i < p) ce_u32(v[i], v[p]);
-        }
-#pragma unroll
-        for (int j = k >> 2; j > 0; j >>= 1) {
-#pragma unroll
-            for (int i = 0; i < EPL; ++i)
-                if ((i & j) == 0) ce_u32(v[i], v[i | j]);
-        }
-    }
-}
-
-// xor stages with lane masks jl_first, jl_first/2, .., 1 followed by the in-lane tail
-template <int EPL>
-__device__ __forceinline__ void warp_merge_tail(u32 (&v)[EPL], const int lane, const int jl_first) {
-#pragma unroll 1
-    for (int jl = jl_first; jl > 0; jl >>= 1) {
-        const bool lower = (lane & jl) == 0;
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-            const u32 o = __shfl_xor_sync(0xffffffffu, v[i], jl);
-            v[i] = lower ? min(v[i], o) : max(v[i], o);
-        }
-    }
-    lane_tail<EPL>(v);
-}
-
-template <int EPL>
-__device__ __forceinline__ void warp_bitonic_sort(u32 (&v)[EPL], const int lane) {
-    lane_sort<EPL>(v);
-#pragma unroll 1
-    for (int kl = 2; kl <= 32; kl <<= 1) {  // merges across kl lanes
-        {   // mirror stage: partner lane = lane ^ (kl-1), partner register = EPL-1-i
-            const bool lower = (lane & (kl >> 1)) == 0;
-            u32 o[EPL];
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) o[i] = __shfl_xor_sync(0xffffffffu, v[EPL - 1 - i], kl - 1);
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) v[i] = lower ? min(v[i], o[i]) : max(v[i], o[i]);
-        }
-        warp_merge_tail<EPL>(v, lane, kl >> 2);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -163,7 +91,7 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
             v[i] = f32_sortable(__double2float_rn(x - x0));
         }
         if (bad) atomicOr(status, ST_NONFINITE);
-        warp_bitonic_sort<32>(v, lane);
+        warp_bitonic_sort<32, u32>(v, lane);
     }
     for (int k = 2048; k <= S; k <<= 1) {  // merge levels wider than one warp
         for (int j = k; j >= 2048; j >>= 1) {  // j == k: mirror stage (g ^ (k-1)); else xor stage (g ^ j/2)
@@ -183,7 +111,7 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
                 }
             }
         }
-        if (wid < W) warp_merge_tail<32>(v, lane, 16);  // strides 512 .. 1 stay inside the warp
+        if (wid < W) warp_merge_tail<32, u32>(v, lane, 16);  // strides 512 .. 1 stay inside the warp
     }
     __syncthreads();
     if (wid < W) {
@@ -432,7 +360,7 @@ __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u
         }
         v[k] = key;
     }
-    warp_bitonic_sort<EPL>(v, lane);
+    warp_bitonic_sort<EPL, u32>(v, lane);
 
     // equal-key neighbours (collisions of distinct values or true ties) are rare: detect them on registers
     const u32 prev_lane = __shfl_up_sync(0xffffffffu, v[EPL - 1], 1);

@@ -193,20 +193,51 @@ def test_strict_tcgen05_gram_bit_exact(engine, oracle, T, n, seed, maker):
         engine.set_option(E.OPT_BD_IMPL, E.BD_AUTO)
 
 
-def test_strict_auto_selects_by_survivor_rate(engine, oracle):
-    """SD_BD_AUTO probes 8 queries with the bit kernel: crossing curves stay on it, non-crossing curves
-    (about half of all pairs survive every mask word) switch to the data-independent tcgen05 Gram."""
+def test_strict_auto_policy(engine, oracle):
+    """SD_BD_AUTO: tie-free queries are answered by sign-vector matching; queries with ties fall back to an
+    enumerating kernel -- the bit kernel, or the tcgen05 Gram when a probe shows that the bit kernel would
+    drown in survivors.  Every route gives the oracle's counts."""
     from statdepth_b200 import _engine as E
     rng = np.random.default_rng(23)
     T, n = 96, 1300
     q = np.arange(0, n, 13)  # 100 queries
-    X = rng.standard_normal((T, n)).cumsum(0)
-    assert (engine.band_depth_counts(X, q, 2, False) == oracle.bd_counts(X, q)).all()
-    assert engine.timings()["bd_impl_used"] == E.BD_BITS
-    Xn = np.outer(rng.random(T) + 0.1, rng.random(n))
-    assert (engine.band_depth_counts(Xn, q, 2, False) == oracle.bd_counts(Xn, q)).all()
-    assert engine.timings()["bd_impl_used"] == E.BD_GEMM
-    assert (engine.band_depth_counts(Xn, None, 2, False)[q] == oracle.bd_counts(Xn, q)).all()
+    walk = rng.standard_normal((T, n)).cumsum(0)
+    smooth = np.outer(rng.random(T) + 0.1, rng.random(n))           # non-crossing, tie-free
+    cases = [(walk, E.BD_MATCH), (smooth, E.BD_MATCH),
+             (np.round(walk), E.BD_BITS),                            # ties, few survivors
+             (np.round(smooth * 8.0), E.BD_GEMM)]                    # ties, ~half of all pairs survive
+    for X, used in cases:
+        exp = oracle.bd_counts(X, q)
+        assert (engine.band_depth_counts(X, q, 2, False) == exp).all()
+        assert engine.timings()["bd_impl_used"] == used
+    for impl in (E.BD_BITS, E.BD_GEMM, E.BD_MATCH):
+        try:
+            engine.set_option(E.OPT_BD_IMPL, impl)
+            for X, _ in cases[:3]:
+                assert (engine.band_depth_counts(X, q[:40], 2, False) == oracle.bd_counts(X, q[:40])).all()
+        finally:
+            engine.set_option(E.OPT_BD_IMPL, E.BD_AUTO)
+    assert (engine.band_depth_counts(smooth, None, 2, False)[q] == oracle.bd_counts(smooth, q)).all()
+
+
+def test_strict_match_edge_shapes(engine, oracle):
+    """Sign-vector matcher on ragged shapes: T not a multiple of 32, n = 3 .. 8193, a few tied curves (set Z)."""
+    from statdepth_b200 import _engine as E
+    rng = np.random.default_rng(29)
+    try:
+        engine.set_option(E.OPT_BD_IMPL, E.BD_MATCH)
+        for T, n in ((1, 3), (5, 6), (33, 70), (100, 513), (37, 1025), (64, 2500)):
+            X = rng.standard_normal((T, n)).cumsum(0)
+            assert (engine.band_depth_counts(X, None, 2, False) == oracle.bd_counts(X)).all()
+            X[:, 1] = X[:, 0]                    # curve 1 duplicates curve 0: ties for queries 0 and 1 only
+            X[T // 2, 2::7] = X[T // 2, 0]       # a few curves touch curve 0 once
+            assert (engine.band_depth_counts(X, None, 2, False) == oracle.bd_counts(X)).all()
+        X = rng.standard_normal((40, 8193)).cumsum(0)  # largest n the matcher takes
+        qs = [0, 4096, 8192]
+        assert (engine.band_depth_counts(X, qs, 2, False) == oracle.bd_counts(X, qs)).all()
+        assert engine.timings()["bd_impl_used"] == E.BD_MATCH
+    finally:
+        engine.set_option(E.OPT_BD_IMPL, E.BD_AUTO)
 
 
 def test_strict_j3(engine, oracle):
