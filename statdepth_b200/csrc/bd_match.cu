@@ -52,17 +52,16 @@ __global__ void __launch_bounds__(128) bd_sig_kernel(const double *__restrict__ 
     __shared__ double sq[32][BM_SQ];
     __shared__ i64 sqi[BM_SQ];
     const int q0 = blockIdx.y * BM_SQ;
-    if (threadIdx.x < BM_SQ) sqi[threadIdx.x] = q0 + threadIdx.x < nqb ? qidx[q0 + threadIdx.x] : 0;
+    if (threadIdx.x < BM_SQ) sqi[threadIdx.x] = q0 + threadIdx.x < nqb ? qidx[q0 + threadIdx.x] : -1;
     const i64 m = n - 1;
-    const i64 o = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = o < m;
+    // one thread per CURVE c; for query q it is other curve o = c - [c > q] (and nothing when c == q)
+    const i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c < n;
     u64 hb[BM_SQ], hc[BM_SQ];
-    bool shift[BM_SQ], tiefree[BM_SQ];
-    __syncthreads();
+    bool tiefree[BM_SQ];
 #pragma unroll
     for (int qq = 0; qq < BM_SQ; ++qq) {
         hb[qq] = hc[qq] = 0x243F6A8885A308D3ull;
-        shift[qq] = o >= sqi[qq];
         tiefree[qq] = true;
     }
     bool bad = false;
@@ -71,7 +70,7 @@ __global__ void __launch_bounds__(128) bd_sig_kernel(const double *__restrict__ 
         for (int i = threadIdx.x; i < 32 * BM_SQ; i += blockDim.x) {
             const int tt = i / BM_SQ, qq = i % BM_SQ;
             const i64 t = (i64)w * 32 + tt;
-            sq[tt][qq] = (t < T && q0 + qq < nqb) ? X[t * ld + sqi[qq]] : 0.0;
+            sq[tt][qq] = (t < T && sqi[qq] >= 0) ? X[t * ld + sqi[qq]] : 0.0;
         }
         __syncthreads();
         if (!live) continue;
@@ -80,13 +79,13 @@ __global__ void __launch_bounds__(128) bd_sig_kernel(const double *__restrict__ 
         u32 b[BM_SQ], a[BM_SQ];
 #pragma unroll
         for (int qq = 0; qq < BM_SQ; ++qq) b[qq] = a[qq] = 0u;
+        const double *col = X + (i64)w * 32 * ld + c;
+#pragma unroll 4
         for (int tt = 0; tt < tmax; ++tt) {
-            const double *row = X + ((i64)w * 32 + tt) * ld;
-            const double x0 = row[o], x1 = row[o + 1];
-            bad |= !isfinite(x0) || !isfinite(x1);
+            const double x = col[(i64)tt * ld];
+            bad |= !isfinite(x);
 #pragma unroll
             for (int qq = 0; qq < BM_SQ; ++qq) {
-                const double x = shift[qq] ? x1 : x0;
                 const double xq = sq[tt][qq];
                 b[qq] |= (u32)(x < xq) << tt;
                 a[qq] |= (u32)(x > xq) << tt;
@@ -94,7 +93,8 @@ __global__ void __launch_bounds__(128) bd_sig_kernel(const double *__restrict__ 
         }
 #pragma unroll
         for (int qq = 0; qq < BM_SQ; ++qq) {
-            if (q0 + qq < nqb) Mw[((i64)(q0 + qq) * W + w) * m + o] = make_uint2(b[qq], a[qq]);
+            const i64 qi = sqi[qq];
+            if (qi >= 0 && c != qi) Mw[((i64)(q0 + qq) * W + w) * m + (c - (c > qi))] = make_uint2(b[qq], a[qq]);
             hb[qq] = bm_mix(hb[qq], b[qq]);
             hc[qq] = bm_mix(hc[qq], ~b[qq] & valid);
             tiefree[qq] = tiefree[qq] && ((b[qq] | a[qq]) == valid);
@@ -103,11 +103,14 @@ __global__ void __launch_bounds__(128) bd_sig_kernel(const double *__restrict__ 
     if (bad) atomicOr(status, ST_NONFINITE);
     if (!live) return;
 #pragma unroll
-    for (int qq = 0; qq < BM_SQ; ++qq)
-        if (q0 + qq < nqb) {
+    for (int qq = 0; qq < BM_SQ; ++qq) {
+        const i64 qi = sqi[qq];
+        if (qi >= 0 && c != qi) {
+            const i64 o = c - (c > qi);
             sig[(i64)(q0 + qq) * m + o] = make_ulonglong2(bm_final(hb[qq]), bm_final(hc[qq]));
             tf[(i64)(q0 + qq) * m + o] = tiefree[qq] ? 1 : 0;
         }
+    }
 }
 
 __device__ __forceinline__ int bm_swz(int g) { return g ^ ((g >> 4) & 15); }
@@ -309,7 +312,7 @@ int bd_strict_match_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, 
     for (i64 q0 = 0; q0 < nq; q0 += QB) {
         const int nqb = (int)(nq - q0 < QB ? nq - q0 : QB);
         SD_TRY(prof_begin(ctx, SD_PHASE_BD_MASKS));
-        bd_sig_kernel<<<dim3((unsigned)ceil_div(m, 128), (unsigned)ceil_div(nqb, BM_SQ)), 128, 0, st>>>(
+        bd_sig_kernel<<<dim3((unsigned)ceil_div(n, 128), (unsigned)ceil_div(nqb, BM_SQ)), 128, 0, st>>>(
             dX, T, n, ld, d_q + q0, nqb, (int)W, Mw, sig, tf, ctx->d_status);
         SD_TRY(prof_end(ctx));
         SD_TRY(prof_begin(ctx, SD_PHASE_BD_PAIRS));
