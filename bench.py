@@ -330,10 +330,12 @@ def main():
     if not relax:
         # strict BD: int8-tensor-equivalent dense work 2*(2T)*C(n-1,2) ops per depth-eval
         ops = 2.0 * (2 * T) * comb(n - 1, 2) * nq_local
-        roof = {"bound": "tensor", "achieved": ops / kern_s / 1e12, "peak": 4500.0, "unit": "TOP/s (int8 dense-equivalent)",
-                "frac": ops / kern_s / 1e12 / 4500.0, "traffic": None,
-                "peak_source": "nominal int8 dense (not measured); the bit-mask kernel skips work by early exit, "
-                               "so this is a dense-EQUIVALENT rate, not tensor-pipe utilisation",
+        i8_peak = eng.probe_int8_peak() / 1e12
+        roof = {"bound": "tensor", "achieved": ops / kern_s / 1e12, "peak": i8_peak, "unit": "TOP/s (int8 dense-equivalent)",
+                "frac": ops / kern_s / 1e12 / i8_peak, "traffic": None,
+                "peak_source": "measured here: sd_probe_int8_peak (tcgen05.mma kind::i8 issue loop, operands resident in "
+                               "shared memory; nominal dense is 4500).  Only --bd-impl gemm does this many operations; "
+                               "for bits / match the figure is a dense-EQUIVALENT rate (they skip the work)",
                 "kernel_ms_per_step": kern_s * 1e3,
                 "phase_ms_per_step": {k: v / 1e6 / args.steps for k, v in phases.items()}}
 

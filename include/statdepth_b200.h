@@ -119,6 +119,9 @@ int sd_get_timings(sd_ctx *ctx, sd_timings *out);
 /* with SD_OPT_PROFILE on: device nanoseconds per phase (enum sd_phase) of the LAST call, summed over
  * its launches of that phase; out must hold SD_PHASE_COUNT entries. */
 int sd_get_phase_ns(sd_ctx *ctx, int64_t *out);
+/* micro-benchmark: sustained tcgen05.mma kind::i8 rate of this GPU in int8 ops/s (2 per MAC), the measured
+ * denominator for the Gram kernel's roofline fraction (takes ~10 ms) */
+int sd_probe_int8_peak(sd_ctx *ctx, double *ops_per_s);
 /* the context's cudaStream_t (as void*), so a caller can order its own work / events on it */
 void *sd_stream(sd_ctx *ctx);
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "sd_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "sd_get_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "sd_get_phase_ns": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sd_probe_int8_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "sd_stream": (C.c_void_p, [C.c_void_p]),
     "sd_band_depth_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p,
                                     C.c_int64, C.c_int, C.c_int, C.c_void_p]),
@@ -153,6 +154,12 @@ class Engine:
         out = np.zeros(len(PHASES), dtype=np.int64)
         self._check(self.lib.sd_get_phase_ns(self._ctx, _ptr(out)))
         return {k: int(v) for k, v in zip(PHASES, out) if v}
+
+    def probe_int8_peak(self) -> float:
+        """Measured tcgen05 kind::i8 rate of this GPU, int8 ops/s."""
+        v = C.c_double()
+        self._check(self.lib.sd_probe_int8_peak(self._ctx, C.byref(v)))
+        return float(v.value)
 
     def set_option(self, option: int, value: int):
         self._check(self.lib.sd_set_option(self._ctx, int(option), int(value)))

@@ -320,6 +320,94 @@ __global__ void __launch_bounds__(GM_THREADS, 2) bd_gram_kernel(const uint8_t *_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// int8 tensor-pipe probe: how fast can this chip retire tcgen05.mma.kind::i8 (M = 128, N = 128 or 256,
+// K = 32) when nothing else is in the way?  One CTA per SM (or two), one thread issues `iters` MMAs on
+// operand tiles that stay in shared memory, one commit, one wait.  Gives the MEASURED denominator for the
+// Gram kernel's roofline fraction (MEASURED_PEAKS.json only has bf16).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) i8_peak_kernel(const int iters, const int ncols) {
+    extern __shared__ __align__(1024) uint8_t pk_smem[];  // A tile 16 KB | B tile 32 KB (zeros are fine)
+    __shared__ __align__(8) u64 done_bar;
+    __shared__ u32 tmem_holder;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(pk_smem)[i] = make_uint4(0x01010101u, 0x01000100u, 0u, 0x01010101u);
+    if (threadIdx.x == 0) {
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                     "r"((u32)ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> async proxy (MMA)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tmem_base = tmem_holder;
+    if (warp == 1 && lane == 0) {
+        const u32 a0 = smem_u32(pk_smem), b0 = a0 + 16384;
+        // N = ncols: B tile has ncols rows -> chunk plane = ncols * 16 bytes
+        const u32 planeB = (u32)ncols * 16u;
+        const u32 idesc = (2u << 4) | ((u32)(ncols >> 3) << 17) | ((u32)(GM_TILE >> 4) << 24);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                u64 da = umma_desc(a0 + k * 2 * GM_CHUNK_PLANE);
+                u64 db = 0;
+                db |= (u64)(((b0 + k * 2 * planeB) >> 4) & 0x3fffu);
+                db |= (u64)((planeB >> 4) & 0x3fffu) << 16;
+                db |= (u64)((128u >> 4) & 0x3fffu) << 32;
+                db |= (u64)1 << 46;
+                tc_mma_i8(tmem_base, da, db, idesc, (u32)((it | k) != 0));
+            }
+        }
+        tc_commit(&done_bar);
+        mbar_wait(&done_bar, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((u32)ncols)
+                     : "memory");
+    }
+}
+
+// best of {N = 128, N = 256} x {1, 2 CTAs per SM}; returns int8 ops/s (2 ops per MAC)
+int probe_int8_peak(sd_ctx *ctx, double *ops_per_s) {
+    cudaStream_t st = ctx->stream;
+    const size_t smem = 16384 + 32768;
+    SD_CUDA(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    SD_CUDA(cudaEventCreate(&e0));
+    SD_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    const int iters = 4000;
+    for (int ncols = 128; ncols <= 256; ncols <<= 1) {
+        for (int per_sm = 1; per_sm <= 2; ++per_sm) {
+            const int grid = ctx->sm_count * per_sm;
+            i8_peak_kernel<<<grid, 128, smem, st>>>(200, ncols);  // warm-up
+            SD_CUDA(cudaEventRecord(e0, st));
+            i8_peak_kernel<<<grid, 128, smem, st>>>(iters, ncols);
+            SD_CUDA(cudaEventRecord(e1, st));
+            SD_CUDA(cudaStreamSynchronize(st));
+            SD_CUDA(cudaGetLastError());
+            float ms = 0.f;
+            SD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            const double ops = 2.0 * 128.0 * (double)ncols * 32.0 * 4.0 * (double)iters * (double)grid;
+            const double rate = ops / ((double)ms * 1e-3);
+            if (rate > best) best = rate;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ops_per_s = best;
+    return SD_OK;
+}
+
 __global__ void iota_i64_kernel2(i64 *p, i64 count) {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) p[i] = i;

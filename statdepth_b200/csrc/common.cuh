@@ -128,6 +128,7 @@ int bd_strict_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const 
                      i64 *d_out, u64 *d_hits = nullptr);
 int bd_strict_gemm_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq,
                           i64 *d_out);
+int probe_int8_peak(sd_ctx *ctx, double *ops_per_s);
 bool bd_match_supported(i64 T, i64 n);
 int bd_strict_match_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq, i64 *d_out,
                            int (*fallback)(sd_ctx *, const double *, i64, i64, i64, const i64 *, i64, i64 *),

@@ -310,6 +310,15 @@ int sd_get_phase_ns(sd_ctx *ctx, int64_t *out) {
     return SD_OK;
 }
 
+int sd_probe_int8_peak(sd_ctx *ctx, double *ops_per_s) {
+    if (!ctx || !ops_per_s) {
+        sd::set_error("sd_probe_int8_peak: NULL argument");
+        return SD_ERR_INVALID;
+    }
+    SD_CUDA(cudaSetDevice(ctx->device));
+    return sd::probe_int8_peak(ctx, ops_per_s);
+}
+
 void *sd_stream(sd_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 }  // extern "C"
