@@ -248,16 +248,26 @@ def test_strict_j3(engine, oracle):
 
 
 def test_strict_full_size_sample(engine, oracle):
-    """BASELINE config 3 (8192 curves x 512 points): all 8192 queries on the GPU, 48 of them checked
-    against the oracle; plus the bound count <= C(n-1,2)."""
+    """BASELINE config 3 (8192 curves x 512 points): all 8192 queries on the GPU (sign-vector matcher), 48 of
+    them checked against the oracle, and three independent GPU algorithms cross-checked on larger samples:
+    matcher == bit kernel on 256 queries == tcgen05 Gram on 64 queries; plus the bound count <= C(n-1,2)."""
+    from statdepth_b200 import _engine as E
     T, n = 512, 8192
     X = walks(2, T, n)
     got = engine.band_depth_counts(X, None, 2, False)
-    q = np.random.default_rng(0).choice(n, 48, replace=False)
+    assert engine.timings()["bd_impl_used"] == E.BD_MATCH
+    rng = np.random.default_rng(0)
+    q = rng.choice(n, 48, replace=False)
     assert (got[q] == oracle.bd_counts(X, q)).all()
     assert got.max() <= comb(n - 1, 2) and got.min() >= 0
-    sub = engine.band_depth_counts(X, q, 2, False)
-    assert (sub == got[q]).all()
+    q2 = rng.choice(n, 256, replace=False)
+    try:
+        engine.set_option(E.OPT_BD_IMPL, E.BD_BITS)
+        assert (engine.band_depth_counts(X, q2, 2, False) == got[q2]).all()
+        engine.set_option(E.OPT_BD_IMPL, E.BD_GEMM)
+        assert (engine.band_depth_counts(X, q2[:64], 2, False) == got[q2[:64]]).all()
+    finally:
+        engine.set_option(E.OPT_BD_IMPL, E.BD_AUTO)
 
 
 # ------------------------------------------------------------------------------------------------
