@@ -41,6 +41,7 @@ constexpr int OVERSAMPLE = 32;     // sample elements per part
 constexpr int KEY_BITS = 22;       // reduced key bits (10 low bits carry the slot id)
 constexpr u32 KEY_MAX = (1u << KEY_BITS) - 1u;
 constexpr int FB_TILE = 4096;      // keys sorted in shared memory by the fallback
+constexpr int PT_BUCKETS = 1024;   // partition: equal-width lookup table over the splitter range
 
 __device__ __forceinline__ i64 comb2_dev(i64 m) { return m * (m - 1) / 2; }
 __device__ __forceinline__ i64 comb3_dev(i64 m) {
@@ -70,8 +71,10 @@ __device__ __forceinline__ int sp_swz(int g) { return g ^ ((g >> 5) & 31); }
 __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double *__restrict__ X, i64 n, i64 ld,
                                                                    int P, int S, double *__restrict__ splitters,
                                                                    float *__restrict__ splitters_f,
+                                                                   unsigned short *__restrict__ tables,
                                                                    int *__restrict__ status) {
     __shared__ u32 skey[MAX_SAMPLE];
+    __shared__ float s_splf[MAX_PARTS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int W = S >> 10;  // warps that hold samples
     const double *xr = X + (i64)blockIdx.x * ld;
@@ -126,7 +129,27 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
     for (int p = tid + 1; p < P; p += SP_THREADS) {
         const float f = f32_unsortable(skey[sp_swz((int)(((i64)p * S) / P))]);
         outf[p - 1] = f;
+        s_splf[p - 1] = f;
         out[p - 1] = x0 + (double)f;
+    }
+    __syncthreads();
+    // lookup table for the partition kernel: tbl[b] = #splitters < lower edge of equal-width bucket b over
+    // [first splitter, last splitter]; built once per row here instead of once per partition CTA
+    const int nspl = P - 1;
+    const float f_first = s_splf[0];
+    const float w = (s_splf[nspl - 1] - f_first) * (1.0f / PT_BUCKETS);
+    const bool usable = w > 0.f && w < INFINITY;
+    int top = 1;
+    while (top < P) top <<= 1;
+    unsigned short *tbl = tables + (i64)blockIdx.x * PT_BUCKETS;
+    for (int b = tid; b < PT_BUCKETS; b += SP_THREADS) {
+        const float edge = f_first + (float)b * w;
+        int lo = 0;
+        for (int step = top >> 1; step > 0; step >>= 1) {
+            const int probe = lo + step;
+            if (probe <= nspl && s_splf[probe - 1] < edge) lo = probe;
+        }
+        tbl[b] = (unsigned short)(usable ? lo : 0);
     }
 }
 
@@ -140,7 +163,6 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
 constexpr int PT_THREADS = 256;
 constexpr int PT_EPT = 16;                      // values per thread
 constexpr int PT_CHUNK = PT_THREADS * PT_EPT;   // 4096 values per CTA
-constexpr int PT_BUCKETS = 1024;                // equal-width lookup table over the splitter range
 constexpr size_t PT_SMEM = (size_t)PT_CHUNK * 8 + (size_t)PT_CHUNK * 4 + (size_t)MAX_PARTS * 4 * 3 +
                            (size_t)(PT_BUCKETS + 8) * 2 + 64;
 
@@ -160,6 +182,7 @@ __device__ __forceinline__ int part_of(const float f, const float *__restrict__ 
 
 __global__ void __launch_bounds__(PT_THREADS) mbd_partition_kernel(const double *__restrict__ X, i64 n, i64 ld, int P,
                                                                    const float *__restrict__ splitters_f,
+                                                                   const unsigned short *__restrict__ tables,
                                                                    int *__restrict__ cursor, int *__restrict__ rowflag,
                                                                    double *__restrict__ part_x,
                                                                    u32 *__restrict__ part_j, i64 row_stride,
@@ -180,25 +203,14 @@ __global__ void __launch_bounds__(PT_THREADS) mbd_partition_kernel(const double 
     const int nspl = P - 1;
     for (int i = tid; i < nspl; i += PT_THREADS) splf[i] = splitters_f[(i64)row * nspl + i];
     for (int i = tid; i < P; i += PT_THREADS) pre[i] = 0;
+    for (int b = tid; b < PT_BUCKETS; b += PT_THREADS) tbl[b] = nspl > 0 ? tables[(i64)row * PT_BUCKETS + b] : 0;
     __syncthreads();
     float f_first = 0.f, inv_w = 0.f;
     if (nspl > 0) {
         f_first = splf[0];
         const float w = (splf[nspl - 1] - f_first) * (1.0f / PT_BUCKETS);
         if (w > 0.f && w < INFINITY) inv_w = 1.0f / w;
-        int top = 1;
-        while (top < P) top <<= 1;
-        for (int b = tid; b < PT_BUCKETS; b += PT_THREADS) {  // tbl[b] = #splitters < lower edge of bucket b
-            const float edge = f_first + (float)b * w;
-            int lo = 0;
-            for (int step = top >> 1; step > 0; step >>= 1) {
-                const int probe = lo + step;
-                if (probe <= nspl && splf[probe - 1] < edge) lo = probe;
-            }
-            tbl[b] = (unsigned short)(inv_w > 0.f ? lo : 0);
-        }
     }
-    __syncthreads();
     const i64 c0 = (i64)blockIdx.x * PT_CHUNK;
     const int len = (n - c0) < PT_CHUNK ? (int)(n - c0) : PT_CHUNK;
 
@@ -674,13 +686,15 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     SD_TRY(ctx->buf[BUF_PART_X].reserve((size_t)Tc * row_stride * 8));
     SD_TRY(ctx->buf[BUF_PART_J].reserve((size_t)Tc * row_stride * 4));
     SD_TRY(ctx->buf[BUF_CURSOR].reserve((size_t)Tc * (P + 1) * sizeof(int)));
-    SD_TRY(ctx->buf[BUF_SPLIT].reserve((size_t)Tc * (P > 1 ? P - 1 : 1) * (sizeof(double) + sizeof(float))));
+    SD_TRY(ctx->buf[BUF_SPLIT].reserve((size_t)Tc * (P > 1 ? P - 1 : 1) * (sizeof(double) + sizeof(float)) +
+                                       (size_t)Tc * PT_BUCKETS * sizeof(unsigned short)));
     double *part_x = ctx->buf[BUF_PART_X].as<double>();
     u32 *part_j = ctx->buf[BUF_PART_J].as<u32>();
     int *cursor = ctx->buf[BUF_CURSOR].as<int>();
     int *rowflag = cursor + (size_t)Tc * P;
     double *splitters = ctx->buf[BUF_SPLIT].as<double>();
     float *splitters_f = reinterpret_cast<float *>(splitters + (size_t)Tc * (P > 1 ? P - 1 : 1));
+    unsigned short *tables = reinterpret_cast<unsigned short *>(splitters_f + (size_t)Tc * (P > 1 ? P - 1 : 1));
     int *fb_count = ctx->d_status + 1;
     SD_TRY(ctx->buf[BUF_WORK].reserve((size_t)Tc * P * sizeof(int2)));
     int2 *biglist = ctx->buf[BUF_WORK].as<int2>();
@@ -707,14 +721,15 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             if (P > 1) {
                 SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SPLITTERS));
                 mbd_splitters_kernel<<<(unsigned)rows, SP_THREADS, 0, st>>>(Xb, n, ld, P, S, splitters, splitters_f,
-                                                                            ctx->d_status);
+                                                                            tables, ctx->d_status);
                 SD_TRY(prof_end(ctx));
                 ctx->last.launches++;
             }
             dim3 pgrid((unsigned)ceil_div(n, PT_CHUNK), (unsigned)rows);
             SD_TRY(prof_begin(ctx, SD_PHASE_MBD_PARTITION));
-            mbd_partition_kernel<<<pgrid, PT_THREADS, PT_SMEM, st>>>(Xb, n, ld, P, splitters_f, cursor, rowflag,
-                                                                     part_x, part_j, row_stride, ctx->d_status);
+            mbd_partition_kernel<<<pgrid, PT_THREADS, PT_SMEM, st>>>(Xb, n, ld, P, splitters_f, tables, cursor,
+                                                                     rowflag, part_x, part_j, row_stride,
+                                                                     ctx->d_status);
             SD_TRY(prof_end(ctx));
             ctx->last.launches++;
             const i64 nwarps = rows * P;
