@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdepth.so")
+LIB_PATH = os.environ.get("STATDEPTH_B200_LIB", os.path.join(_HERE, "libsdepth.so"))  # override: tuning builds
 
 SD_OK = 0
 STATUS_NAMES = {1: "SD_ERR_INVALID", 2: "SD_ERR_CUDA", 3: "SD_ERR_NO_DEVICE", 4: "SD_ERR_NONFINITE",

@@ -14,7 +14,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libsdepth.so")
+LIB = os.path.join(HERE, "libsdepth%s.so" % os.environ.get("SD_LIB_SUFFIX", ""))
+OBJ_SUFFIX = os.environ.get("SD_LIB_SUFFIX", "")
+EXTRA = os.environ.get("SD_EXTRA_NVCC_FLAGS", "").split()
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -60,10 +62,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_one(item):
         src, extra = item
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        o = os.path.join(OBJ, src.replace(".cu", OBJ_SUFFIX + ".o"))
         if not force and os.path.exists(o) and os.path.getmtime(o) >= max(os.path.getmtime(s), headers_m):
             return o
-        cmd = [nvcc] + ARCH + COMMON + extra + ["-c", s, "-o", o]
+        cmd = [nvcc] + ARCH + COMMON + extra + EXTRA + ["-c", s, "-o", o]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

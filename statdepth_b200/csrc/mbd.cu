@@ -160,11 +160,17 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
 //    coalesced stores.  (v1 did one global atomic + two scattered 8/4-byte stores per value and
 //    was bound by L2 atomic / sector-write throughput: 2.1 ms of a 4.2 ms step.)
 // ---------------------------------------------------------------------------------------------
-constexpr int PT_THREADS = 256;
-constexpr int PT_EPT = 16;                      // values per thread
+#ifndef SD_PT_THREADS
+#define SD_PT_THREADS 256
+#endif
+#ifndef SD_PT_EPT
+#define SD_PT_EPT 16
+#endif
+constexpr int PT_THREADS = SD_PT_THREADS;
+constexpr int PT_EPT = SD_PT_EPT;               // values per thread
 constexpr int PT_CHUNK = PT_THREADS * PT_EPT;   // 4096 values per CTA
 constexpr size_t PT_SMEM = (size_t)PT_CHUNK * 8 + (size_t)PT_CHUNK * 4 + (size_t)MAX_PARTS * 4 * 3 +
-                           (size_t)(PT_BUCKETS + 8) * 2 + 64;
+                           (size_t)(PT_BUCKETS + 8) * 2 + 256;
 
 // part of a value = number of splitters <= f, f = float(x - x[0]).  Every step is monotone in x, so
 // equal values share a part and parts are ordered.  The lookup table only provides a starting guess
@@ -180,7 +186,7 @@ __device__ __forceinline__ int part_of(const float f, const float *__restrict__ 
     return idx;
 }
 
-__global__ void __launch_bounds__(PT_THREADS) mbd_partition_kernel(const double *__restrict__ X, i64 n, i64 ld, int P,
+__global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_partition_kernel(const double *__restrict__ X, i64 n, i64 ld, int P,
                                                                    const float *__restrict__ splitters_f,
                                                                    const unsigned short *__restrict__ tables,
                                                                    int *__restrict__ cursor, int *__restrict__ rowflag,
