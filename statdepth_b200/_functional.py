@@ -78,6 +78,9 @@ def _multivariate_depths(data: List[pd.DataFrame], queries: np.ndarray, relax: b
     if d > 3:
         raise NotImplementedError('simplex containment is implemented for d <= 3 channels on the B200 engine')
     tol = settings.get_simplex_tolerance()
+    if not (d == 2 and relax and N > 64):  # relaxed 2-D depth above 64 curves is counted per (query, time point)
+        settings.check_enumeration(float(len(queries)) * binom(N - 1, d + 1) * (T if relax else 1.0),
+                                   'multivariate simplex depth (d=%d, N=%d, relax=%s)' % (d, N, relax))
     cnt = _dist.query_sharded(lambda qb: eng.simplex_depth_counts(F, qb, relax, tol), queries, np.int64)
     s = cnt.astype(np.float64)
     if relax:

@@ -42,6 +42,8 @@ def _pointwisedepth(
             raise NotImplementedError('simplicial depth is implemented for d <= 3 on the B200 engine')
         q = _positions(to_compute, data.index, 'to_compute')
         tol = settings.get_simplex_tolerance()
+        if d != 2 or n <= 256:  # 2-D clouds above 256 points are counted, not enumerated
+            settings.check_enumeration(float(len(q)) * binom(n - 1, d + 1), 'simplicial depth (d=%d, n=%d)' % (d, n))
         cnt = _dist.query_sharded(lambda qb: eng.simplicial_counts(P, qb, tol), q, np.int64)
         return pd.Series(index=to_compute, data=cnt.astype(np.float64) / binom(n, d + 1))
     elif containment == 'l1':
@@ -66,6 +68,7 @@ def _pointwisedepth(
         q = _positions(idx, data.index, 'to_compute')
         # reference quirk (:182-183,191-193): with to_compute the subsets are drawn from to_compute only
         pool = None if to_compute is None else q
+        settings.check_enumeration(float(len(q)) * binom(n if pool is None else len(pool), d), 'Oja depth (d=%d)' % d)
         vals = _dist.query_sharded(lambda qb: eng.oja(P, hull_volume, qb, pool), q, np.float64)
         # reference quirk (:205): index=to_compute, i.e. a default RangeIndex when to_compute is None
         return pd.Series(index=to_compute, data=vals)

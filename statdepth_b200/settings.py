@@ -17,3 +17,26 @@ def set_simplex_tolerance(tol: float) -> None:
     if not tol >= 0.0:
         raise ValueError("tolerance must be >= 0")
     _SIMPLEX_TOL = tol
+
+
+# Largest enumeration (subsets x queries [x time points]) the engine will start.  Simplicial depth in 2-D and
+# relaxed multivariate simplex depth in 2-D are COUNTED (O(n log n) per query) and never hit this limit; d = 3,
+# strict multivariate depth and Oja depth enumerate C(n-1, k) subsets per query like the reference does.
+_MAX_ENUMERATION = 5e13
+
+
+def get_max_enumeration() -> float:
+    return _MAX_ENUMERATION
+
+
+def set_max_enumeration(limit: float) -> None:
+    global _MAX_ENUMERATION
+    _MAX_ENUMERATION = float(limit)
+
+
+def check_enumeration(work: float, what: str) -> None:
+    if work > _MAX_ENUMERATION:
+        raise NotImplementedError(
+            '%s would enumerate %.3g simplices; the B200 engine enumerates like the reference for this case and '
+            'refuses more than %.3g (statdepth_b200.settings.set_max_enumeration raises the limit)'
+            % (what, work, _MAX_ENUMERATION))

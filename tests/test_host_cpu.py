@@ -151,3 +151,23 @@ def test_permutation_test_batched_equals_loop(host_on_oracle, monkeypatch):
             b = permutation_test(F, G, method=method, B=12, seed=3, relax=relax, batched=False)
             assert a["observed"] == b["observed"] and a["p_value"] == b["p_value"]
             assert a["null"].tolist() == b["null"].tolist()
+
+
+def test_enumeration_guard(host_on_oracle):
+    """Cases the engine can only enumerate (d = 3, strict multivariate, Oja) refuse oversized jobs up front;
+    2-D simplicial depth and relaxed 2-D multivariate depth are counted and have no such limit."""
+    from statdepth_b200 import settings
+    rng = np.random.default_rng(0)
+    old = settings.get_max_enumeration()
+    try:
+        settings.set_max_enumeration(1e4)
+        with pytest.raises(NotImplementedError, match='enumerate'):
+            PointcloudDepth(pd.DataFrame(rng.standard_normal((30, 3))), containment='simplex')
+        with pytest.raises(NotImplementedError, match='enumerate'):
+            PointcloudDepth(pd.DataFrame(rng.standard_normal((60, 2))), containment='oja')
+        curves = [pd.DataFrame(rng.standard_normal((4, 2))) for _ in range(20)]
+        with pytest.raises(NotImplementedError, match='enumerate'):
+            FunctionalDepth(curves, containment='simplex', relax=False)
+        assert len(PointcloudDepth(pd.DataFrame(rng.standard_normal((12, 2))), containment='simplex')) == 12
+    finally:
+        settings.set_max_enumeration(old)
