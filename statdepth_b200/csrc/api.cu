@@ -190,7 +190,7 @@ using namespace sd;
 
 extern "C" {
 
-int sd_band_depth_f64(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_t ld, int layout,
+static int sd_band_depth_f64_impl(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_t ld, int layout,
                       const int64_t *query_idx, int64_t nq, int j, int relax, int64_t *count_out) {
     SD_TRY(check_common(ctx, X, count_out, "sd_band_depth_f64"));
     SD_REQUIRE(T >= 1 && n >= 1 && nq >= 0, "sd_band_depth_f64: bad sizes T=%lld n=%lld nq=%lld", (long long)T,
@@ -224,7 +224,7 @@ int sd_band_depth_f64(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_
     return end_call(ctx, true);
 }
 
-int sd_band_depth_f64_dev(sd_ctx *ctx, const double *dX, int64_t T, int64_t n, int64_t ld,
+static int sd_band_depth_f64_dev_impl(sd_ctx *ctx, const double *dX, int64_t T, int64_t n, int64_t ld,
                           const int64_t *d_query_idx, int64_t nq, int j, int relax, int64_t *d_count_out) {
     SD_TRY(check_common(ctx, dX, d_count_out, "sd_band_depth_f64_dev"));
     SD_REQUIRE(T >= 1 && n >= 1 && nq >= 0 && ld >= n, "sd_band_depth_f64_dev: bad sizes");
@@ -361,7 +361,7 @@ int sd_pointcloud_oja_f64(sd_ctx *ctx, const double *P, int64_t n, int d, const 
 }
 
 
-int sd_band_depth_batched_f64(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_t ld,
+static int sd_band_depth_batched_f64_impl(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_t ld,
                               const uint8_t *membership, int64_t B, const int64_t *queries, int64_t nqb, int j,
                               int relax, int64_t *count_out) {
     SD_TRY(check_common(ctx, X, count_out, "sd_band_depth_batched_f64"));
@@ -415,6 +415,37 @@ int sd_band_depth_batched_f64(sd_ctx *ctx, const double *X, int64_t T, int64_t n
         SD_CUDA(cudaMemcpyAsync(count_out, d_out, qloc.size() * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
     // cols / qloc are pageable host vectors: the async copies above were staged synchronously
     return end_call(ctx, true);
+}
+
+int sd_band_depth_f64(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_t ld, int layout,
+                      const int64_t *query_idx, int64_t nq, int j, int relax, int64_t *count_out) {
+    try {
+        return sd_band_depth_f64_impl(ctx, X, T, n, ld, layout, query_idx, nq, j, relax, count_out);
+    } catch (...) {  // std::bad_alloc from host-side staging vectors: the ABI never throws
+        sd::set_error("sd_band_depth_f64: out of host memory");
+        return SD_ERR_INVALID;
+    }
+}
+
+int sd_band_depth_f64_dev(sd_ctx *ctx, const double *dX, int64_t T, int64_t n, int64_t ld,
+                          const int64_t *d_query_idx, int64_t nq, int j, int relax, int64_t *d_count_out) {
+    try {
+        return sd_band_depth_f64_dev_impl(ctx, dX, T, n, ld, d_query_idx, nq, j, relax, d_count_out);
+    } catch (...) {  // std::bad_alloc from host-side staging vectors: the ABI never throws
+        sd::set_error("sd_band_depth_f64_dev: out of host memory");
+        return SD_ERR_INVALID;
+    }
+}
+
+int sd_band_depth_batched_f64(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_t ld,
+                              const uint8_t *membership, int64_t B, const int64_t *queries, int64_t nqb, int j,
+                              int relax, int64_t *count_out) {
+    try {
+        return sd_band_depth_batched_f64_impl(ctx, X, T, n, ld, membership, B, queries, nqb, j, relax, count_out);
+    } catch (...) {  // std::bad_alloc from host-side staging vectors: the ABI never throws
+        sd::set_error("sd_band_depth_batched_f64: out of host memory");
+        return SD_ERR_INVALID;
+    }
 }
 
 }  // extern "C"
