@@ -20,9 +20,11 @@
 //                             registers with a shuffle bitonic network, resolves equal-key runs with
 //                             exact fp64 compares, and adds term(b, a) to acc[curve] with a 64-bit RED.
 //      mbd_rank_big_kernel  : persistent; drains the work list of parts with 513..1024 values.
-//   4. mbd_fallback_kernel  : rows in which some part overflowed CAP (heavy ties, adversarial
-//                             distributions) are ranked by a generic one-CTA-per-row bitonic sort of
-//                             order-preserving u64 keys + binary-search ranks.  Correct for any
+//      mbd_heavy_kernel     : parts with more than CAP values hold a few heavily repeated values (ties):
+//                             ranked from a per-part table of at most 8 distinct values, no sorting.
+//   4. mbd_fallback_kernel  : rows in which a part of more than CAP values holds more than 8 distinct values
+//                             (adversarial spreads) are ranked by a generic one-CTA-per-row bitonic
+//                             sort of order-preserving u64 keys + binary-search ranks.  Correct for any
 //                             finite input; slower.
 // HBM layout: X[t*ld + c] float64 (time-major rows are contiguous and streamed with coalesced
 // loads); acc int64[n]; part lists [row][part][CAP] float64 + uint32.
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_par
                 off[p0 + k] = g - base;
                 base += cnt[k];
             }
-        if (over) rowflag[row] = 1;
+        if (over) atomicOr(&rowflag[row], 1);  // bit 0: some part holds more than CAP values
     }
     __syncthreads();
 
@@ -338,13 +340,85 @@ __device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, u32 
     }
 }
 
-// skeys / sres: this warp's shared scratch (CAP words each).
+// Runs of equal 22-bit keys in a sorted part (collisions of distinct values, or true ties).  The caller has
+// published the sorted keys (position pos = lane*EPL + i at skeys[i*32 + lane]) and zeroed sflag.  Every
+// position finds its run start with a max-scan over head positions; the run's last element records the run
+// length and every element that differs from the run's first value flags the run.  A run of one repeated
+// value (tie-heavy data; any length) then costs O(1) per element; only a run that mixes distinct values
+// under one key is counted pairwise.  Kept out of line: it is rare and must not cost the sort registers.
+template <int EPL>
+__device__ __noinline__ void resolve_runs(const double *__restrict__ px, const int cnt, const u32 *skeys, u32 *sres,
+                                          u32 *sflag, const int lane) {
+    const int p0 = lane * EPL;
+    const u32 r_before = p0 > 0 && p0 <= cnt ? skeys[((p0 - 1) % EPL) * 32 + (p0 - 1) / EPL] >> 10 : 0xffffffffu;
+    int last_head = -1;  // last run start inside this lane's chunk
+    u32 rp = r_before;
+#pragma unroll 1
+    for (int i = 0; i < EPL && p0 + i < cnt; ++i) {
+        const u32 r = skeys[i * 32 + lane] >> 10;
+        if (r != rp) last_head = p0 + i;
+        rp = r;
+    }
+    int carry = last_head;  // inclusive max-scan over lanes, then shifted by one lane
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, carry, d);
+        if (lane >= d) carry = max(carry, up);
+    }
+    carry = __shfl_up_sync(0xffffffffu, carry, 1);
+    if (lane == 0) carry = 0;
+    int rs = carry;
+    rp = r_before;
+#pragma unroll 1
+    for (int i = 0; i < EPL && p0 + i < cnt; ++i) {
+        const int pos = p0 + i;
+        const u32 k = skeys[i * 32 + lane];
+        const u32 r = k >> 10;
+        if (r != rp) rs = pos;
+        rp = r;
+        const u32 rn = pos + 1 < cnt ? skeys[((pos + 1) % EPL) * 32 + (pos + 1) / EPL] >> 10 : 0xffffffffu;
+        u32 mark = rn != r ? (u32)(pos + 1 - rs) : 0u;  // run length, recorded by the run's last element
+        if (rs != pos) {
+            const u32 k0 = skeys[(rs % EPL) * 32 + rs / EPL];
+            if (!(px[k & 1023u] == px[k0 & 1023u])) mark |= 0x80000000u;  // the run holds distinct values
+        }
+        if (mark) atomicOr(&sflag[(rs % EPL) * 32 + rs / EPL], mark);
+    }
+    __syncwarp();
+    rs = carry;
+    rp = r_before;
+#pragma unroll 1
+    for (int i = 0; i < EPL && p0 + i < cnt; ++i) {
+        const int pos = p0 + i;
+        const u32 k = skeys[i * 32 + lane];
+        const u32 r = k >> 10;
+        if (r != rp) rs = pos;
+        rp = r;
+        const u32 f = sflag[(rs % EPL) * 32 + rs / EPL];
+        const int len = (int)(f & 0x7fffffffu);
+        if (len == 1) continue;  // not in a run: written by the caller's fast path
+        const int slot = (int)(k & 1023u);
+        int less = 0, greater = 0;
+        if (f & 0x80000000u) {  // mixed run: exact pairwise counting inside the run
+            const double xs = px[slot];
+            for (int m = rs; m < rs + len; ++m) {
+                const double xm = px[skeys[(m % EPL) * 32 + m / EPL] & 1023u];
+                less += xm < xs;
+                greater += xm > xs;
+            }
+        }
+        sres[slot] = (u32)(rs + less) | ((u32)(rs + len - greater) << 16);
+    }
+}
+
+// skeys / sres / sflag: this warp's shared scratch (CAP words each).
 // [lo, hi): value range of the part when it is known from the splitters (interior parts); otherwise
 // (first / last part, single-part rows) have_range is false and the range is measured.
 template <int EPL>
 __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u32 *__restrict__ pj, const int cnt,
                                           const u32 base, const i64 row_global, const RankOut &o, u32 *skeys,
-                                          u32 *sres, const int lane, double lo, double hi, const bool have_range) {
+                                          u32 *sres, u32 *sflag, const int lane, double lo, double hi,
+                                          const bool have_range) {
     const u32 n32 = (u32)o.n;
     if (!have_range) {
         lo = INFINITY;
@@ -365,18 +439,27 @@ __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u
     }
     // monotone 22-bit key | slot id.  lo <= x (exactly), every step below is monotone in x.
     const double scale = (double)KEY_MAX / (hi - lo);
+    const double x_first = EPL == 32 ? px[0] : 0.0;
+    bool all_equal = true;  // only tested for the rare > CAP/2 parts, which tie-heavy rows produce in numbers
     u32 v[EPL];
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
         const int s = lane + 32 * k;
         u32 key = 0xffffffffu;
         if (s < cnt) {
-            const double t = (px[s] - lo) * scale;
+            const double xv = px[s];
+            if (EPL == 32) all_equal &= xv == x_first;
+            const double t = (xv - lo) * scale;
             u32 r = (u32)__double2uint_rz(t);  // NaN (inf*0) converts to 0: still consistent, resolved by the run scan
             r = min(r, KEY_MAX);
             key = (r << 10) | (u32)s;
         }
         v[k] = key;
+    }
+    if (EPL == 32 && __all_sync(0xffffffffu, all_equal)) {  // one value class: no sort needed
+#pragma unroll 1
+        for (int s = lane; s < cnt; s += 32) emit_rank(o, row_global, pj[s], base, n32 - base - (u32)cnt);
+        return;
     }
     warp_bitonic_sort<EPL, u32>(v, lane);
 
@@ -397,41 +480,13 @@ __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u
         if (pos < cnt && !in_run) sres[v[i] & 1023u] = (u32)pos | ((u32)(pos + 1) << 16);
     }
     if (__any_sync(0xffffffffu, any_run)) {
-        // slow path: publish the sorted keys (pos = lane*EPL + i at skeys[i*32 + lane]) and let every
-        // element of a run count, with exact fp64 compares, its run mates below / above it
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) skeys[i * 32 + lane] = v[i];
-        __syncwarp();
-#pragma unroll 1
         for (int i = 0; i < EPL; ++i) {
-            const int pos = lane * EPL + i;
-            if (pos >= cnt) break;
-            const u32 key = skeys[i * 32 + lane];
-            const u32 r = key >> 10;
-            const bool left = pos > 0 && (skeys[((pos - 1) % EPL) * 32 + (pos - 1) / EPL] >> 10) == r;
-            const bool right = pos + 1 < cnt && (skeys[((pos + 1) % EPL) * 32 + (pos + 1) / EPL] >> 10) == r;
-            if (!(left || right)) continue;
-            const int slot = (int)(key & 1023u);
-            const double xs = px[slot];
-            int rs = pos, re = pos + 1, less = 0, greater = 0;
-            for (int m = pos - 1; m >= 0; --m) {
-                const u32 km = skeys[(m % EPL) * 32 + m / EPL];
-                if ((km >> 10) != r) break;
-                const double xm = px[km & 1023u];
-                less += xm < xs;
-                greater += xm > xs;
-                rs = m;
-            }
-            for (int m = pos + 1; m < cnt; ++m) {
-                const u32 km = skeys[(m % EPL) * 32 + m / EPL];
-                if ((km >> 10) != r) break;
-                const double xm = px[km & 1023u];
-                less += xm < xs;
-                greater += xm > xs;
-                re = m + 1;
-            }
-            sres[slot] = (u32)(rs + less) | ((u32)(re - greater) << 16);
+            skeys[i * 32 + lane] = v[i];
+            sflag[i * 32 + lane] = 0u;
         }
+        __syncwarp();
+        resolve_runs<EPL>(px, cnt, skeys, sres, sflag, lane);
     }
     __syncwarp();
 #pragma unroll 1
@@ -451,7 +506,7 @@ struct RankArgs {
     int P;
     i64 nwarps;                // rows * P
     const int *cursor;         // [rows][P] fill counts
-    const int *rowflag;        // [rows] 1 = row overflowed, generic path takes it
+    const int *rowflag;        // [rows] bit 0: has parts with > CAP values (all-equal classes), bit 1: generic path
     const double *splitters;   // [rows][P-1]
     const double *part_x;      // [rows][row_stride]
     const u32 *part_j;
@@ -462,7 +517,7 @@ struct RankArgs {
 
 template <int EPL>
 __device__ __forceinline__ void rank_one(const RankArgs &a, const RankOut &o, const i64 row, const int part,
-                                         const int cnt, u32 *skeys, u32 *sres, const int lane) {
+                                         const int cnt, u32 *skeys, u32 *sres, u32 *sflag, const int lane) {
     const int P = a.P;
     const int *cur = a.cursor + row * P;
     u32 base = 0;
@@ -478,7 +533,7 @@ __device__ __forceinline__ void rank_one(const RankArgs &a, const RankOut &o, co
     }
     const double *px = a.part_x + row * a.row_stride + (i64)part * CAP;
     const u32 *pj = a.part_j + row * a.row_stride + (i64)part * CAP;
-    rank_part<EPL>(px, pj, cnt, base, a.row0 + row, o, skeys, sres, lane, lo, hi, have_range);
+    rank_part<EPL>(px, pj, cnt, base, a.row0 + row, o, skeys, sres, sflag, lane, lo, hi, have_range);
 }
 
 // One warp per (row, part) for parts of at most CAP/2 values (8 or 16 keys per lane, 56 registers);
@@ -487,26 +542,28 @@ __device__ __forceinline__ void rank_one(const RankArgs &a, const RankOut &o, co
 __global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_kernel(const RankArgs a, const RankOut o) {
     __shared__ u32 s_keys[RANK_WARPS][CAP / 2];
     __shared__ u32 s_res[RANK_WARPS][CAP / 2];
+    __shared__ u32 s_flag[RANK_WARPS][CAP / 2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const i64 w = (i64)blockIdx.x * RANK_WARPS + wid;
     if (w >= a.nwarps) return;
     const i64 row = w / a.P;
     const int part = (int)(w - row * a.P);
-    if (a.rowflag[row]) return;  // the whole row goes to the generic path
+    if (a.rowflag[row] & 2) return;  // the whole row goes to the generic path
     const int cnt = a.cursor[row * a.P + part];
-    if (cnt == 0) return;
+    if (cnt == 0 || cnt > CAP) return;  // heavy parts (one value repeated > CAP times): mbd_heavy_kernel
     if (cnt > CAP / 2) {
         if (lane == 0) a.biglist[atomicAdd(&a.bigcount[0], 1)] = make_int2((int)row, part);
         return;
     }
-    if (cnt <= 256) rank_one<8>(a, o, row, part, cnt, s_keys[wid], s_res[wid], lane);
-    else rank_one<16>(a, o, row, part, cnt, s_keys[wid], s_res[wid], lane);
+    if (cnt <= 256) rank_one<8>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
+    else rank_one<16>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
 }
 
 // persistent: warps claim entries of the big-part work list
 __global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const RankArgs a, const RankOut o) {
     __shared__ u32 s_keys[RANK_WARPS][CAP];
     __shared__ u32 s_res[RANK_WARPS][CAP];
+    __shared__ u32 s_flag[RANK_WARPS][CAP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int total = a.bigcount[0];
     for (;;) {
@@ -515,7 +572,148 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const 
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= total) break;
         const int2 e = a.biglist[i];
-        rank_one<32>(a, o, (i64)e.x, e.y, a.cursor[(i64)e.x * a.P + e.y], s_keys[wid], s_res[wid], lane);
+        rank_one<32>(a, o, (i64)e.x, e.y, a.cursor[(i64)e.x * a.P + e.y], s_keys[wid], s_res[wid], s_flag[wid], lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3b. heavy parts: a part with more than CAP values can only arise when few VALUES are repeated very often
+//     (equal values always share a part; distinct values are spread by the equal-mass splitters).  Such a
+//     part needs no sorting.  One CTA per row that has heavy parts, run BEFORE the rank kernels:
+//       pass 1  every value of a heavy part is entered in the part's table of at most HV_VALUES distinct
+//               values (shared memory) and counted; a part with more distinct values, or more than HV_PARTS
+//               heavy parts, hands the whole row to the generic path (bit 1) and nothing is emitted;
+//       pass 2  each member gets b = #values in lower parts + #smaller values of its part, a likewise.
+//     Members are found by re-running the part lookup on the row (the part lists only keep CAP values).
+// ---------------------------------------------------------------------------------------------
+constexpr int HV_PARTS = 128;
+constexpr int HV_VALUES = 8;
+constexpr int HV_THREADS = 1024;
+constexpr int HV_UNROLL = 4;
+constexpr u64 HV_EMPTY = ~0ull;  // a NaN pattern: never equals the canonical bits of a finite value
+
+__device__ __forceinline__ int hv_find(const volatile u64 *tab, const u64 bits) {
+#pragma unroll
+    for (int k = 0; k < HV_VALUES; ++k)
+        if (tab[k] == bits) return k;
+    return -1;
+}
+
+__global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__restrict__ X, const i64 n, const i64 ld,
+                                                        const int P, const float *__restrict__ splitters_f,
+                                                        const unsigned short *__restrict__ tables,
+                                                        const int *__restrict__ cursor, int *__restrict__ rowflag,
+                                                        const i64 row0, const RankOut o) {
+    __shared__ float splf[MAX_PARTS];
+    __shared__ unsigned short tbl[PT_BUCKETS];
+    __shared__ int cnt[MAX_PARTS];
+    __shared__ u32 base[MAX_PARTS];
+    __shared__ short hidx[MAX_PARTS];
+    __shared__ u64 tab[HV_PARTS][HV_VALUES];
+    __shared__ int tcnt[HV_PARTS][HV_VALUES];
+    __shared__ int tbelow[HV_PARTS][HV_VALUES];
+    __shared__ int s_bad, s_heavy;
+    const int row = blockIdx.x, tid = threadIdx.x;
+    if ((rowflag[row] & 3) != 1) return;  // no heavy part, or already generic
+    const int nspl = P - 1;
+    const double *xr = X + (i64)row * ld;
+    const double x0 = xr[0];
+    for (int i = tid; i < nspl; i += blockDim.x) splf[i] = splitters_f[(i64)row * nspl + i];
+    for (int b = tid; b < PT_BUCKETS; b += blockDim.x) tbl[b] = nspl > 0 ? tables[(i64)row * PT_BUCKETS + b] : 0;
+    for (int p = tid; p < P; p += blockDim.x) cnt[p] = cursor[(i64)row * P + p];
+    for (int i = tid; i < HV_PARTS * HV_VALUES; i += blockDim.x) {
+        (&tab[0][0])[i] = HV_EMPTY;
+        (&tcnt[0][0])[i] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {  // P <= 1024: a serial prefix is cheap next to the scans of the row
+        u32 run = 0;
+        int heavy = 0;
+        for (int p = 0; p < P; ++p) {
+            base[p] = run;
+            run += (u32)cnt[p];
+            hidx[p] = -1;
+            if (cnt[p] > CAP) {
+                if (heavy < HV_PARTS) hidx[p] = (short)heavy;
+                ++heavy;
+            }
+        }
+        s_heavy = heavy;
+        s_bad = heavy > HV_PARTS;
+    }
+    float f_first = 0.f, inv_w = 0.f;
+    if (nspl > 0) {
+        f_first = splf[0];
+        const float w = (splf[nspl - 1] - f_first) * (1.0f / PT_BUCKETS);
+        if (w > 0.f && w < INFINITY) inv_w = 1.0f / w;
+    }
+    __syncthreads();
+    if (!s_bad) {
+        for (i64 c0 = tid; c0 < n; c0 += (i64)HV_UNROLL * blockDim.x) {
+            double xs[HV_UNROLL];  // loads first: the row scan is latency bound with one CTA per row
+#pragma unroll
+            for (int u = 0; u < HV_UNROLL; ++u) {
+                const i64 c = c0 + (i64)u * blockDim.x;
+                xs[u] = c < n ? xr[c] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < HV_UNROLL; ++u) {
+                if (c0 + (i64)u * blockDim.x >= n) break;
+                const double x = xs[u];
+                const int part = nspl > 0 ? part_of(__double2float_rn(x - x0), splf, nspl, tbl, f_first, inv_w) : 0;
+                const int h = hidx[part];
+                if (h < 0) continue;
+                const u64 bits = (u64)__double_as_longlong(x + 0.0);  // -0.0 and +0.0 are one value
+                int k = hv_find(tab[h], bits);
+                if (k < 0) {  // not yet entered: claim the first free entry (or meet a racing equal entry)
+                    for (k = 0; k < HV_VALUES; ++k) {
+                        const u64 old = atomicCAS((unsigned long long *)&tab[h][k], HV_EMPTY, bits);
+                        if (old == HV_EMPTY || old == bits) break;
+                    }
+                    if (k == HV_VALUES) {
+                        s_bad = 1;
+                        continue;
+                    }
+                }
+                atomicAdd(&tcnt[h][k], 1);
+            }
+        }
+    }
+    __syncthreads();
+    if (s_bad) {
+        if (tid == 0) atomicOr(&rowflag[row], 2);
+        return;
+    }
+    for (int i = tid; i < s_heavy * HV_VALUES; i += blockDim.x) {
+        const int h = i / HV_VALUES, k = i % HV_VALUES;
+        int below = 0;
+        if (tcnt[h][k] > 0) {
+            const double vk = __longlong_as_double((long long)tab[h][k]);
+            for (int m = 0; m < HV_VALUES; ++m)
+                if (tcnt[h][m] > 0 && __longlong_as_double((long long)tab[h][m]) < vk) below += tcnt[h][m];
+        }
+        tbelow[h][k] = below;
+    }
+    __syncthreads();
+    for (i64 c0 = tid; c0 < n; c0 += (i64)HV_UNROLL * blockDim.x) {
+        double xs[HV_UNROLL];
+#pragma unroll
+        for (int u = 0; u < HV_UNROLL; ++u) {
+            const i64 c = c0 + (i64)u * blockDim.x;
+            xs[u] = c < n ? xr[c] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < HV_UNROLL; ++u) {
+            const i64 c = c0 + (i64)u * blockDim.x;
+            if (c >= n) break;
+            const double x = xs[u];
+            const int part = nspl > 0 ? part_of(__double2float_rn(x - x0), splf, nspl, tbl, f_first, inv_w) : 0;
+            const int h = hidx[part];
+            if (h < 0) continue;
+            const int k = hv_find(tab[h], (u64)__double_as_longlong(x + 0.0));
+            const u32 b = base[part] + (u32)tbelow[h][k];
+            emit_rank(o, row0 + row, (u32)c, b, (u32)n - b - (u32)tcnt[h][k]);
+        }
     }
 }
 
@@ -565,7 +763,7 @@ __global__ void __launch_bounds__(1024) mbd_fallback_kernel(const double *__rest
                                                              int *__restrict__ status, int *__restrict__ fb_count) {
     __shared__ u64 tile[FB_TILE];
     const i64 row = blockIdx.x;
-    if (!rowflag[row]) return;
+    if (!(rowflag[row] & 2)) return;
     const int tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) atomicAdd(fb_count, 1);
     const double *xr = X + row * ld;
@@ -720,7 +918,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         const i64 rows = T - r0 < Tc ? T - r0 : Tc;
         const double *Xb = dX + r0 * ld;
         if (ctx->mbd_force_fallback) {
-            fill_int_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(rowflag, rows, 1);
+            fill_int_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(rowflag, rows, 2);
             ctx->last.launches++;
         } else {
             SD_CUDA(cudaMemsetAsync(cursor, 0, (size_t)Tc * (P + 1) * sizeof(int), st));
@@ -740,6 +938,8 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             ctx->last.launches++;
             const i64 nwarps = rows * P;
             SD_TRY(prof_begin(ctx, SD_PHASE_MBD_RANK));
+            // rows with parts of more than CAP values (heavy ties): those parts are ranked from value tables
+            mbd_heavy_kernel<<<(unsigned)rows, HV_THREADS, 0, st>>>(Xb, n, ld, P, splitters_f, tables, cursor, rowflag, r0, o);
             RankArgs ra;
             ra.P = P;
             ra.nwarps = nwarps;
@@ -756,7 +956,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             mbd_rank_kernel<<<(unsigned)ceil_div(nwarps, RANK_WARPS), RANK_WARPS * 32, 0, st>>>(ra, o);
             mbd_rank_big_kernel<<<(unsigned)(ctx->sm_count * 4), RANK_WARPS * 32, 0, st>>>(ra, o);
             SD_TRY(prof_end(ctx));
-            ctx->last.launches += 2;
+            ctx->last.launches += 3;
         }
         // rows flagged as overflowing (or all rows when forced): generic path; idle CTAs exit at once
         SD_TRY(prof_begin(ctx, SD_PHASE_MBD_GENERIC));

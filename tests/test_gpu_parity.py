@@ -141,10 +141,18 @@ def test_mbd_full_size_properties(engine, oracle):
     assert (sl == oracle.mbd_counts_all(X[500:548])).all()
     depth = full / T / comb(n, 2)
     assert depth.max() <= (n - 2) / n and depth.min() > 0
-    # tie stress at full width: integers -> heavy ties, parts overflow, generic path takes over
+    # tie stress at full width: integers -> value classes of thousands of curves overflow their parts; they are
+    # recognised as single-value classes (no sorting); only rows where an overflowing part mixes several
+    # values still take the generic path
     Xr = np.round(X[:16])
     assert (engine.band_depth_counts(Xr, None, 2, True) == oracle.mbd_counts_all(Xr)).all()
-    assert engine.timings()["fallback_rows"] > 0
+    assert engine.timings()["fallback_rows"] < 16
+    Xc = np.round(X[:8] / 50.0)  # a handful of classes, each far above the part capacity
+    assert (engine.band_depth_counts(Xc, None, 2, True) == oracle.mbd_counts_all(Xc)).all()
+    # an adversarial row: 3000 DISTINCT values squeezed between two sample quantiles cannot be a single class
+    Xa = X[:4].copy()
+    Xa[:, :3000] = Xa[:, [3000]] + np.arange(3000) * 1e-13
+    assert (engine.band_depth_counts(Xa, None, 2, True) == oracle.mbd_counts_all(Xa)).all()
 
 
 # ------------------------------------------------------------------------------------------------
