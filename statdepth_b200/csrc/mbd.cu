@@ -504,8 +504,8 @@ constexpr int RANK_WARPS = 4;
 // rare 1024-value case: BIG = false ranks parts with cnt <= 512, BIG = true the others.
 struct RankArgs {
     int P;
-    i64 nwarps;                // rows * P
     const int *cursor;         // [rows][P] fill counts
+    const u32 *pbase;          // [rows][P] exclusive prefix of the fill counts (#values in lower parts)
     const int *rowflag;        // [rows] bit 0: has parts with > CAP values (all-equal classes), bit 1: generic path
     const double *splitters;   // [rows][P-1]
     const double *part_x;      // [rows][row_stride]
@@ -519,11 +519,7 @@ template <int EPL>
 __device__ __forceinline__ void rank_one(const RankArgs &a, const RankOut &o, const i64 row, const int part,
                                          const int cnt, u32 *skeys, u32 *sres, u32 *sflag, const int lane) {
     const int P = a.P;
-    const int *cur = a.cursor + row * P;
-    u32 base = 0;
-    for (int p = lane; p < part; p += 32) base += (u32)cur[p];
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) base += __shfl_xor_sync(0xffffffffu, base, s);
+    const u32 base = a.pbase[row * P + part];
     // interior parts: [splitter[part-1], splitter[part]) bounds the values of the part
     const bool have_range = part > 0 && part < P - 1;
     double lo = 0.0, hi = 0.0;
@@ -544,10 +540,9 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_kernel(const Rank
     __shared__ u32 s_res[RANK_WARPS][CAP / 2];
     __shared__ u32 s_flag[RANK_WARPS][CAP / 2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const i64 w = (i64)blockIdx.x * RANK_WARPS + wid;
-    if (w >= a.nwarps) return;
-    const i64 row = w / a.P;
-    const int part = (int)(w - row * a.P);
+    const i64 row = blockIdx.y;  // grid: (parts / RANK_WARPS, rows)
+    const int part = blockIdx.x * RANK_WARPS + wid;
+    if (part >= a.P) return;
     if (a.rowflag[row] & 2) return;  // the whole row goes to the generic path
     const int cnt = a.cursor[row * a.P + part];
     if (cnt == 0 || cnt > CAP) return;  // heavy parts (one value repeated > CAP times): mbd_heavy_kernel
@@ -579,7 +574,8 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const 
 // ---------------------------------------------------------------------------------------------
 // 3b. heavy parts: a part with more than CAP values can only arise when few VALUES are repeated very often
 //     (equal values always share a part; distinct values are spread by the equal-mass splitters).  Such a
-//     part needs no sorting.  One CTA per row that has heavy parts, run BEFORE the rank kernels:
+//     part needs no sorting.  One CTA per row, run BEFORE the rank kernels; it first writes the row's
+//     exclusive prefix of part sizes (pbase) for them, and rows without heavy parts stop there.  Otherwise:
 //       pass 1  every value of a heavy part is entered in the part's table of at most HV_VALUES distinct
 //               values (shared memory) and counted; a part with more distinct values, or more than HV_PARTS
 //               heavy parts, hands the whole row to the generic path (bit 1) and nothing is emitted;
@@ -603,7 +599,7 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
                                                         const int P, const float *__restrict__ splitters_f,
                                                         const unsigned short *__restrict__ tables,
                                                         const int *__restrict__ cursor, int *__restrict__ rowflag,
-                                                        const i64 row0, const RankOut o) {
+                                                        u32 *__restrict__ pbase, const i64 row0, const RankOut o) {
     __shared__ float splf[MAX_PARTS];
     __shared__ unsigned short tbl[PT_BUCKETS];
     __shared__ int cnt[MAX_PARTS];
@@ -613,25 +609,49 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
     __shared__ int tcnt[HV_PARTS][HV_VALUES];
     __shared__ int tbelow[HV_PARTS][HV_VALUES];
     __shared__ int s_bad, s_heavy;
+    __shared__ u32 s_wsum[HV_THREADS / 32];
     const int row = blockIdx.x, tid = threadIdx.x;
+    // every row: exclusive prefix of the part sizes (#values in lower parts) for the rank kernels
+    const u32 mycnt = tid < P ? (u32)cursor[(i64)row * P + tid] : 0u;
+    u32 incl = mycnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 up = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((tid & 31) >= d) incl += up;
+    }
+    if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        const u32 t = s_wsum[tid];
+        u32 ws = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 up = __shfl_up_sync(0xffffffffu, ws, d);
+            if (tid >= d) ws += up;
+        }
+        s_wsum[tid] = ws - t;
+    }
+    __syncthreads();
+    const u32 mybase = incl - mycnt + s_wsum[tid >> 5];
+    if (tid < P) pbase[(i64)row * P + tid] = mybase;
     if ((rowflag[row] & 3) != 1) return;  // no heavy part, or already generic
     const int nspl = P - 1;
     const double *xr = X + (i64)row * ld;
     const double x0 = xr[0];
     for (int i = tid; i < nspl; i += blockDim.x) splf[i] = splitters_f[(i64)row * nspl + i];
     for (int b = tid; b < PT_BUCKETS; b += blockDim.x) tbl[b] = nspl > 0 ? tables[(i64)row * PT_BUCKETS + b] : 0;
-    for (int p = tid; p < P; p += blockDim.x) cnt[p] = cursor[(i64)row * P + p];
+    if (tid < P) {
+        cnt[tid] = (int)mycnt;
+        base[tid] = mybase;
+    }
     for (int i = tid; i < HV_PARTS * HV_VALUES; i += blockDim.x) {
         (&tab[0][0])[i] = HV_EMPTY;
         (&tcnt[0][0])[i] = 0;
     }
     __syncthreads();
-    if (tid == 0) {  // P <= 1024: a serial prefix is cheap next to the scans of the row
-        u32 run = 0;
+    if (tid == 0) {  // P <= 1024 and only rows with heavy parts get here: a serial pass is cheap
         int heavy = 0;
         for (int p = 0; p < P; ++p) {
-            base[p] = run;
-            run += (u32)cnt[p];
             hidx[p] = -1;
             if (cnt[p] > CAP) {
                 if (heavy < HV_PARTS) hidx[p] = (short)heavy;
@@ -889,13 +909,14 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
 
     SD_TRY(ctx->buf[BUF_PART_X].reserve((size_t)Tc * row_stride * 8));
     SD_TRY(ctx->buf[BUF_PART_J].reserve((size_t)Tc * row_stride * 4));
-    SD_TRY(ctx->buf[BUF_CURSOR].reserve((size_t)Tc * (P + 1) * sizeof(int)));
+    SD_TRY(ctx->buf[BUF_CURSOR].reserve((size_t)Tc * (2 * P + 1) * sizeof(int)));
     SD_TRY(ctx->buf[BUF_SPLIT].reserve((size_t)Tc * (P > 1 ? P - 1 : 1) * (sizeof(double) + sizeof(float)) +
                                        (size_t)Tc * PT_BUCKETS * sizeof(unsigned short)));
     double *part_x = ctx->buf[BUF_PART_X].as<double>();
     u32 *part_j = ctx->buf[BUF_PART_J].as<u32>();
     int *cursor = ctx->buf[BUF_CURSOR].as<int>();
     int *rowflag = cursor + (size_t)Tc * P;
+    u32 *pbase = reinterpret_cast<u32 *>(rowflag + Tc);
     double *splitters = ctx->buf[BUF_SPLIT].as<double>();
     float *splitters_f = reinterpret_cast<float *>(splitters + (size_t)Tc * (P > 1 ? P - 1 : 1));
     unsigned short *tables = reinterpret_cast<unsigned short *>(splitters_f + (size_t)Tc * (P > 1 ? P - 1 : 1));
@@ -936,14 +957,14 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
                                                                      ctx->d_status);
             SD_TRY(prof_end(ctx));
             ctx->last.launches++;
-            const i64 nwarps = rows * P;
             SD_TRY(prof_begin(ctx, SD_PHASE_MBD_RANK));
             // rows with parts of more than CAP values (heavy ties): those parts are ranked from value tables
-            mbd_heavy_kernel<<<(unsigned)rows, HV_THREADS, 0, st>>>(Xb, n, ld, P, splitters_f, tables, cursor, rowflag, r0, o);
+            mbd_heavy_kernel<<<(unsigned)rows, HV_THREADS, 0, st>>>(Xb, n, ld, P, splitters_f, tables, cursor, rowflag, pbase,
+                                                                    r0, o);
             RankArgs ra;
             ra.P = P;
-            ra.nwarps = nwarps;
             ra.cursor = cursor;
+            ra.pbase = pbase;
             ra.rowflag = rowflag;
             ra.splitters = splitters;
             ra.part_x = part_x;
@@ -953,7 +974,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             ra.biglist = biglist;
             ra.bigcount = ctx->d_status + 2;
             SD_CUDA(cudaMemsetAsync(ctx->d_status + 2, 0, 2 * sizeof(int), st));
-            mbd_rank_kernel<<<(unsigned)ceil_div(nwarps, RANK_WARPS), RANK_WARPS * 32, 0, st>>>(ra, o);
+            mbd_rank_kernel<<<dim3((unsigned)ceil_div(P, RANK_WARPS), (unsigned)rows), RANK_WARPS * 32, 0, st>>>(ra, o);
             mbd_rank_big_kernel<<<(unsigned)(ctx->sm_count * 4), RANK_WARPS * 32, 0, st>>>(ra, o);
             SD_TRY(prof_end(ctx));
             ctx->last.launches += 3;
