@@ -128,16 +128,36 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
     // range bound the rank kernel scales its keys with)
     double *out = splitters + (i64)blockIdx.x * (P - 1);
     float *outf = splitters_f + (i64)blockIdx.x * (P - 1);
-    for (int p = tid + 1; p < P; p += SP_THREADS) {
-        const float f = f32_unsortable(skey[sp_swz((int)(((i64)p * S) / P))]);
-        outf[p - 1] = f;
-        s_splf[p - 1] = f;
-        out[p - 1] = x0 + (double)f;
+    const int nspl = P - 1;
+    for (int p = tid + 1; p < P; p += SP_THREADS) s_splf[p - 1] = f32_unsortable(skey[sp_swz((int)(((i64)p * S) / P))]);
+    __syncthreads();
+    // A value repeated so often that it takes several splitter positions (v v v w) gets a part of its own:
+    // the repeats become the next float up (v v+ v+ w), so that [v, v+) holds exactly the values whose
+    // offset rounds to v and the values above v are not lumped with them into one over-full part.
+    float mine[(MAX_PARTS + SP_THREADS - 1) / SP_THREADS];
+#pragma unroll
+    for (int k = 0; k < (MAX_PARTS + SP_THREADS - 1) / SP_THREADS; ++k) {
+        const int i = tid + k * SP_THREADS;
+        float f = 0.f;
+        if (i < nspl) {
+            f = s_splf[i];
+            if (i > 0 && s_splf[i - 1] == f) f = nextafterf(f, INFINITY);
+        }
+        mine[k] = f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < (MAX_PARTS + SP_THREADS - 1) / SP_THREADS; ++k) {
+        const int i = tid + k * SP_THREADS;
+        if (i < nspl) {
+            s_splf[i] = mine[k];
+            outf[i] = mine[k];
+            out[i] = x0 + (double)mine[k];
+        }
     }
     __syncthreads();
     // lookup table for the partition kernel: tbl[b] = #splitters < lower edge of equal-width bucket b over
     // [first splitter, last splitter]; built once per row here instead of once per partition CTA
-    const int nspl = P - 1;
     const float f_first = s_splf[0];
     const float w = (s_splf[nspl - 1] - f_first) * (1.0f / PT_BUCKETS);
     const bool usable = w > 0.f && w < INFINITY;

@@ -155,6 +155,37 @@ def test_mbd_full_size_properties(engine, oracle):
     assert (engine.band_depth_counts(Xa, None, 2, True) == oracle.mbd_counts_all(Xa)).all()
 
 
+def test_mbd_heavy_parts_edge_cases(engine, oracle):
+    """Parts over capacity: value tables (<= 8 distinct values per part, <= 128 such parts per row), -0.0 == +0.0,
+    a mix of heavy classes and a continuous remainder, and the hand-over to the generic path beyond the limits."""
+    rng = np.random.default_rng(31)
+    n = 200_000
+    # 150 value classes of ~1333 copies: more heavy parts than the tables hold -> generic path, same counts
+    Xm = np.stack([rng.permutation(np.arange(n) % 150).astype(np.float64) for _ in range(2)])
+    assert (engine.band_depth_counts(Xm, None, 2, True) == oracle.mbd_counts_all(Xm)).all()
+    assert engine.timings()["fallback_rows"] == 2
+    # zero-inflated rows: a few heavy classes (each far above the part capacity, one of them +-0.0) inside a
+    # continuous sample -> each class gets a part of its own next to normally sorted parts, no generic rows
+    n = 120_000
+    Xh = rng.standard_normal((3, n))
+    Xh[:, : n // 2] = np.round(Xh[:, : n // 2] * 2.0)
+    Xh[1, :5000] = -0.0
+    Xh[1, 5000:9000] = 0.0
+    for r in range(3):
+        Xh[r] = rng.permutation(Xh[r])
+    assert (engine.band_depth_counts(Xh, None, 2, True) == oracle.mbd_counts_all(Xh)).all()
+    assert engine.timings()["fallback_rows"] == 0
+    # many mid-sized classes (hundreds to ~2400 copies) inside a continuous sample: any route, same counts
+    Xg = rng.standard_normal((3, n))
+    Xg[:, : n // 2] = np.round(Xg[:, : n // 2] * 10.0)
+    for r in range(3):
+        Xg[r] = rng.permutation(Xg[r])
+    assert (engine.band_depth_counts(Xg, None, 2, True) == oracle.mbd_counts_all(Xg)).all()
+    # J = 3 and the rank output go through the same emit path
+    cnt3 = engine.band_depth_counts(Xh, None, 3, True)
+    assert (cnt3 == oracle.mbd_counts_all(Xh, j=3)).all()
+
+
 # ------------------------------------------------------------------------------------------------
 # strict band depth (relax=False)
 # ------------------------------------------------------------------------------------------------
