@@ -342,22 +342,32 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 struct RankOut {
-    i64 *acc2, *acc3;      // acc3 may be null
+    u64 *raw2;             // [n] sum over rows of b(b-1) + a(a-1); mbd_finish_kernel turns it into the j = 2 numerator
+    i64 *acc3;             // j = 3 numerator, may be null
     int *rank_b, *rank_a;  // may be null; [row_global*n + c]
     i64 n;
     i64 full2, full3;      // C(n-1,2), C(n-1,3)
 };
 
-// b, a < 2^31: C(m,2) with one 32x32->64 multiply
-__device__ __forceinline__ u64 comb2_u32(u32 m) { return ((u64)m * (u64)(m - 1u)) >> 1; }  // m = 0 -> 0 * (2^32-1) >> 1 = 0
-
+// One (row, curve) result.  The j = 2 term C(n-1,2) - C(b,2) - C(a,2) is accumulated as the raw sum
+// b(b-1) + a(a-1) (two 32x32->64 multiply-adds and one RED; m = 0 gives 0 * (2^32-1) = 0) and finished once
+// per call by mbd_finish_kernel: numerator += rows * C(n-1,2) - raw / 2.  b, a < 2^31.
+// EXTRA = false drops the j = 3 accumulator and the rank output (the common call) at compile time.
+template <bool EXTRA>
 __device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, u32 c, u32 b, u32 a) {
-    atomicAdd((u64 *)&o.acc2[c], (u64)o.full2 - comb2_u32(b) - comb2_u32(a));
-    if (o.acc3) atomicAdd((u64 *)&o.acc3[c], (u64)(o.full3 - comb3_dev((i64)b) - comb3_dev((i64)a)));
-    if (o.rank_b) {
-        o.rank_b[row_global * o.n + c] = (int)b;
-        o.rank_a[row_global * o.n + c] = (int)a;
+    atomicAdd((unsigned long long *)&o.raw2[c], (u64)b * (u64)(b - 1u) + (u64)a * (u64)(a - 1u));
+    if (EXTRA) {
+        if (o.acc3) atomicAdd((u64 *)&o.acc3[c], (u64)(o.full3 - comb3_dev((i64)b) - comb3_dev((i64)a)));
+        if (o.rank_b) {
+            o.rank_b[row_global * o.n + c] = (int)b;
+            o.rank_a[row_global * o.n + c] = (int)a;
+        }
     }
+}
+
+__global__ void mbd_finish_kernel(const u64 *__restrict__ raw2, i64 *__restrict__ acc2, const i64 n, const i64 rows_full2) {
+    const i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) acc2[c] += rows_full2 - (i64)(raw2[c] >> 1);
 }
 
 // Runs of equal 22-bit keys in a sorted part (collisions of distinct values, or true ties).  The caller has
@@ -434,7 +444,7 @@ __device__ __noinline__ void resolve_runs(const double *__restrict__ px, const i
 // skeys / sres / sflag: this warp's shared scratch (CAP words each).
 // [lo, hi): value range of the part when it is known from the splitters (interior parts); otherwise
 // (first / last part, single-part rows) have_range is false and the range is measured.
-template <int EPL>
+template <int EPL, bool EXTRA>
 __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u32 *__restrict__ pj, const int cnt,
                                           const u32 base, const i64 row_global, const RankOut &o, u32 *skeys,
                                           u32 *sres, u32 *sflag, const int lane, double lo, double hi,
@@ -453,7 +463,7 @@ __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u
         hi = warp_max(hi);
         if (lo == hi) {  // every element ties: b = everything in lower parts, a = everything in higher parts
 #pragma unroll 1
-            for (int s = lane; s < cnt; s += 32) emit_rank(o, row_global, pj[s], base, n32 - base - (u32)cnt);
+            for (int s = lane; s < cnt; s += 32) emit_rank<EXTRA>(o, row_global, pj[s], base, n32 - base - (u32)cnt);
             return;
         }
     }
@@ -478,7 +488,7 @@ __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u
     }
     if (EPL == 32 && __all_sync(0xffffffffu, all_equal)) {  // one value class: no sort needed
 #pragma unroll 1
-        for (int s = lane; s < cnt; s += 32) emit_rank(o, row_global, pj[s], base, n32 - base - (u32)cnt);
+        for (int s = lane; s < cnt; s += 32) emit_rank<EXTRA>(o, row_global, pj[s], base, n32 - base - (u32)cnt);
         return;
     }
     warp_bitonic_sort<EPL, u32>(v, lane);
@@ -512,7 +522,7 @@ __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u
 #pragma unroll 1
     for (int s = lane; s < cnt; s += 32) {
         const u32 res = sres[s];
-        emit_rank(o, row_global, pj[s], base + (res & 0xffffu), n32 - base - (res >> 16));
+        emit_rank<EXTRA>(o, row_global, pj[s], base + (res & 0xffffu), n32 - base - (res >> 16));
     }
     __syncwarp();
 }
@@ -535,7 +545,7 @@ struct RankArgs {
     int *bigcount;             // [0] entries appended, [1] entries claimed
 };
 
-template <int EPL>
+template <int EPL, bool EXTRA>
 __device__ __forceinline__ void rank_one(const RankArgs &a, const RankOut &o, const i64 row, const int part,
                                          const int cnt, u32 *skeys, u32 *sres, u32 *sflag, const int lane) {
     const int P = a.P;
@@ -549,12 +559,13 @@ __device__ __forceinline__ void rank_one(const RankArgs &a, const RankOut &o, co
     }
     const double *px = a.part_x + row * a.row_stride + (i64)part * CAP;
     const u32 *pj = a.part_j + row * a.row_stride + (i64)part * CAP;
-    rank_part<EPL>(px, pj, cnt, base, a.row0 + row, o, skeys, sres, sflag, lane, lo, hi, have_range);
+    rank_part<EPL, EXTRA>(px, pj, cnt, base, a.row0 + row, o, skeys, sres, sflag, lane, lo, hi, have_range);
 }
 
 // One warp per (row, part) for parts of at most CAP/2 values (8 or 16 keys per lane, 56 registers);
 // bigger parts are appended to a work list for mbd_rank_big_kernel so that the common case is not held
 // to the register / shared-memory budget of the rare 1024-value case.
+template <bool EXTRA>
 __global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_kernel(const RankArgs a, const RankOut o) {
     __shared__ u32 s_keys[RANK_WARPS][CAP / 2];
     __shared__ u32 s_res[RANK_WARPS][CAP / 2];
@@ -570,11 +581,12 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_kernel(const Rank
         if (lane == 0) a.biglist[atomicAdd(&a.bigcount[0], 1)] = make_int2((int)row, part);
         return;
     }
-    if (cnt <= 256) rank_one<8>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
-    else rank_one<16>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
+    if (cnt <= 256) rank_one<8, EXTRA>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
+    else rank_one<16, EXTRA>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
 }
 
 // persistent: warps claim entries of the big-part work list
+template <bool EXTRA>
 __global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const RankArgs a, const RankOut o) {
     __shared__ u32 s_keys[RANK_WARPS][CAP];
     __shared__ u32 s_res[RANK_WARPS][CAP];
@@ -587,7 +599,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const 
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= total) break;
         const int2 e = a.biglist[i];
-        rank_one<32>(a, o, (i64)e.x, e.y, a.cursor[(i64)e.x * a.P + e.y], s_keys[wid], s_res[wid], s_flag[wid], lane);
+        rank_one<32, EXTRA>(a, o, (i64)e.x, e.y, a.cursor[(i64)e.x * a.P + e.y], s_keys[wid], s_res[wid], s_flag[wid], lane);
     }
 }
 
@@ -752,7 +764,7 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
             if (h < 0) continue;
             const int k = hv_find(tab[h], (u64)__double_as_longlong(x + 0.0));
             const u32 b = base[part] + (u32)tbelow[h][k];
-            emit_rank(o, row0 + row, (u32)c, b, (u32)n - b - (u32)tcnt[h][k]);
+            emit_rank<true>(o, row0 + row, (u32)c, b, (u32)n - b - (u32)tcnt[h][k]);
         }
     }
 }
@@ -867,7 +879,7 @@ __global__ void __launch_bounds__(1024) mbd_fallback_kernel(const double *__rest
             const i64 mid = (lo + hi) >> 1;
             if (keys[mid] <= key) lo = mid + 1; else hi = mid;
         }
-        emit_rank(o, row0 + row, (u32)c, (u32)b, (u32)(n - lo));
+        emit_rank<true>(o, row0 + row, (u32)c, (u32)b, (u32)(n - lo));
     }
 }
 
@@ -941,13 +953,15 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     float *splitters_f = reinterpret_cast<float *>(splitters + (size_t)Tc * (P > 1 ? P - 1 : 1));
     unsigned short *tables = reinterpret_cast<unsigned short *>(splitters_f + (size_t)Tc * (P > 1 ? P - 1 : 1));
     int *fb_count = ctx->d_status + 1;
-    SD_TRY(ctx->buf[BUF_WORK].reserve((size_t)Tc * P * sizeof(int2)));
+    SD_TRY(ctx->buf[BUF_WORK].reserve((size_t)Tc * P * sizeof(int2) + (size_t)n * sizeof(u64)));
     int2 *biglist = ctx->buf[BUF_WORK].as<int2>();
+    u64 *raw2 = reinterpret_cast<u64 *>(biglist + (size_t)Tc * P);
+    SD_CUDA(cudaMemsetAsync(raw2, 0, (size_t)n * sizeof(u64), st));
 
     SD_CUDA(cudaFuncSetAttribute(mbd_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
 
     RankOut o;
-    o.acc2 = d_acc2;
+    o.raw2 = raw2;
     o.acc3 = want_j3 ? d_acc3 : nullptr;
     o.rank_b = d_rank_b;
     o.rank_a = d_rank_a;
@@ -994,8 +1008,15 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             ra.biglist = biglist;
             ra.bigcount = ctx->d_status + 2;
             SD_CUDA(cudaMemsetAsync(ctx->d_status + 2, 0, 2 * sizeof(int), st));
-            mbd_rank_kernel<<<dim3((unsigned)ceil_div(P, RANK_WARPS), (unsigned)rows), RANK_WARPS * 32, 0, st>>>(ra, o);
-            mbd_rank_big_kernel<<<(unsigned)(ctx->sm_count * 4), RANK_WARPS * 32, 0, st>>>(ra, o);
+            const dim3 rgrid((unsigned)ceil_div(P, RANK_WARPS), (unsigned)rows);
+            const unsigned bgrid = (unsigned)(ctx->sm_count * 4);
+            if (o.acc3 || o.rank_b) {
+                mbd_rank_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                mbd_rank_big_kernel<true><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+            } else {
+                mbd_rank_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                mbd_rank_big_kernel<false><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+            }
             SD_TRY(prof_end(ctx));
             ctx->last.launches += 3;
         }
@@ -1007,6 +1028,9 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         ctx->last.launches++;
         SD_CUDA(cudaGetLastError());
     }
+    mbd_finish_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(raw2, d_acc2, n, T * o.full2);
+    ctx->last.launches++;
+    SD_CUDA(cudaGetLastError());
     return SD_OK;
 }
 
