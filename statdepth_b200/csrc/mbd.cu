@@ -191,20 +191,39 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
 constexpr int PT_THREADS = SD_PT_THREADS;
 constexpr int PT_EPT = SD_PT_EPT;               // values per thread
 constexpr int PT_CHUNK = PT_THREADS * PT_EPT;   // 4096 values per CTA
-constexpr size_t PT_SMEM = (size_t)PT_CHUNK * 8 + (size_t)PT_CHUNK * 4 + (size_t)MAX_PARTS * 4 * 3 +
+constexpr size_t PT_SMEM = (size_t)PT_CHUNK * 8 + (size_t)PT_CHUNK * 4 + (size_t)(MAX_PARTS * 3 + 4) * 4 +
                            (size_t)(PT_BUCKETS + 8) * 2 + 256;
 
 // part of a value = number of splitters <= f, f = float(x - x[0]).  Every step is monotone in x, so
-// equal values share a part and parts are ordered.  The lookup table only provides a starting guess
-// (first splitter of the value's equal-width bucket); the two short scans make the result exact.
-__device__ __forceinline__ int part_of(const float f, const float *__restrict__ splf, const int nspl,
-                                       const unsigned short *__restrict__ tbl, const float f_first,
-                                       const float inv_w) {
+// equal values share a part and parts are ordered.  sp[] is the row's splitter list padded with sentinels:
+// sp[0] = NaN, sp[1 + i] = splitter i, sp[nspl + 1] = sp[nspl + 2] = NaN (every compare with a sentinel is
+// false, also for f = +-inf, so the scans stop at the ends).  The lookup table only provides
+// a starting guess (first splitter of the value's equal-width bucket); three independent shared loads around
+// the guess settle almost every value, the two scans behind them make the result exact for all.
+constexpr int SPL_PAD = 3;
+__device__ __forceinline__ void fill_splitters(float *sp, const float *__restrict__ row_splitters, const int nspl,
+                                               const int tid, const int nthreads) {
+    for (int i = tid; i < nspl; i += nthreads) sp[1 + i] = row_splitters[i];
+    if (tid == 0) {
+        sp[0] = NAN;
+        sp[nspl + 1] = NAN;
+        sp[nspl + 2] = NAN;
+    }
+}
+
+__device__ __forceinline__ int part_of(const float f, const float *__restrict__ sp, const unsigned short *__restrict__ tbl,
+                                       const float f_first, const float inv_w) {
     float fb = (f - f_first) * inv_w;
     fb = fminf(fmaxf(fb, 0.f), (float)(PT_BUCKETS - 1));  // also maps NaN (inf * 0) to 0
     int idx = tbl[(int)fb];
-    while (idx > 0 && splf[idx - 1] > f) --idx;
-    while (idx < nspl && splf[idx] <= f) ++idx;
+    const float below = sp[idx], s0 = sp[idx + 1], s1 = sp[idx + 2];
+    if (below > f) {  // guess too high (bucket rounding): rare
+        do --idx; while (sp[idx] > f);
+        return idx;
+    }
+    idx += (int)(s0 <= f) + (int)(s1 <= f);
+    if (s1 <= f)  // more than two splitters of this bucket are <= f: rare
+        while (sp[idx + 1] <= f) ++idx;
     return idx;
 }
 
@@ -219,7 +238,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_par
     double *sx = reinterpret_cast<double *>(pt_smem);                 // grouped values
     u32 *sj = reinterpret_cast<u32 *>(sx + PT_CHUNK);                 // grouped (part << 12 | index in chunk)
     float *splf = reinterpret_cast<float *>(sj + PT_CHUNK);           // splitters of this row (float offsets)
-    int *pre = reinterpret_cast<int *>(splf + MAX_PARTS);             // per-part count, then exclusive prefix
+    int *pre = reinterpret_cast<int *>(splf + MAX_PARTS + 4);         // per-part count, then exclusive prefix
     int *off = pre + MAX_PARTS;                                       // global slot base - prefix
     unsigned short *tbl = reinterpret_cast<unsigned short *>(off + MAX_PARTS);  // bucket -> first splitter
     int *wtot = reinterpret_cast<int *>(tbl + PT_BUCKETS + 8);        // warp totals of the scan
@@ -227,37 +246,39 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_par
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int row = blockIdx.y;
     const double *xr = X + (i64)row * ld;
-    const double x0 = xr[0];
     const int nspl = P - 1;
-    for (int i = tid; i < nspl; i += PT_THREADS) splf[i] = splitters_f[(i64)row * nspl + i];
+    const i64 c0 = (i64)blockIdx.x * PT_CHUNK;
+    const int len = (n - c0) < PT_CHUNK ? (int)(n - c0) : PT_CHUNK;
+
+    // A. load (issued before the row's tables are staged, so both latencies overlap), locate the part, claim a
+    //    position inside the CTA's group (shared-memory atomic)
+    double x[PT_EPT];
+    u32 tag[PT_EPT];  // part << 16 | position within (CTA, part)
+#pragma unroll
+    for (int u = 0; u < PT_EPT; ++u) {
+        const int i = u * PT_THREADS + tid;
+        x[u] = i < len ? xr[c0 + i] : 0.0;
+    }
+    const double x0 = xr[0];
+    fill_splitters(splf, splitters_f + (i64)row * nspl, nspl, tid, PT_THREADS);
     for (int i = tid; i < P; i += PT_THREADS) pre[i] = 0;
     for (int b = tid; b < PT_BUCKETS; b += PT_THREADS) tbl[b] = nspl > 0 ? tables[(i64)row * PT_BUCKETS + b] : 0;
     __syncthreads();
     float f_first = 0.f, inv_w = 0.f;
     if (nspl > 0) {
-        f_first = splf[0];
-        const float w = (splf[nspl - 1] - f_first) * (1.0f / PT_BUCKETS);
+        f_first = splf[1];
+        const float w = (splf[nspl] - f_first) * (1.0f / PT_BUCKETS);
         if (w > 0.f && w < INFINITY) inv_w = 1.0f / w;
     }
-    const i64 c0 = (i64)blockIdx.x * PT_CHUNK;
-    const int len = (n - c0) < PT_CHUNK ? (int)(n - c0) : PT_CHUNK;
-
-    // A. load, locate the part, claim a position inside the CTA's group (shared-memory atomic)
-    double x[PT_EPT];
-    u32 tag[PT_EPT];  // part << 16 | position within (CTA, part)
     bool bad = false;
 #pragma unroll
-    for (int u = 0; u < PT_EPT; ++u) {
-        const int i = u * PT_THREADS + tid;
-        x[u] = i < len ? xr[c0 + i] : 0.0;
-        bad |= !isfinite(x[u]);
-    }
+    for (int u = 0; u < PT_EPT; ++u) bad |= !isfinite(x[u]);
 #pragma unroll
     for (int u = 0; u < PT_EPT; ++u) {
         const int i = u * PT_THREADS + tid;
         tag[u] = 0xffffffffu;
         if (i < len) {
-            const int part = nspl > 0 ? part_of(__double2float_rn(x[u] - x0), splf, nspl, tbl, f_first, inv_w) : 0;
+            const int part = nspl > 0 ? part_of(__double2float_rn(x[u] - x0), splf, tbl, f_first, inv_w) : 0;
             tag[u] = ((u32)part << 16) | (u32)atomicAdd(&pre[part], 1);
         }
     }
@@ -632,7 +653,7 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
                                                         const unsigned short *__restrict__ tables,
                                                         const int *__restrict__ cursor, int *__restrict__ rowflag,
                                                         u32 *__restrict__ pbase, const i64 row0, const RankOut o) {
-    __shared__ float splf[MAX_PARTS];
+    __shared__ float splf[MAX_PARTS + SPL_PAD];
     __shared__ unsigned short tbl[PT_BUCKETS];
     __shared__ int cnt[MAX_PARTS];
     __shared__ u32 base[MAX_PARTS];
@@ -670,7 +691,7 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
     const int nspl = P - 1;
     const double *xr = X + (i64)row * ld;
     const double x0 = xr[0];
-    for (int i = tid; i < nspl; i += blockDim.x) splf[i] = splitters_f[(i64)row * nspl + i];
+    fill_splitters(splf, splitters_f + (i64)row * nspl, nspl, tid, blockDim.x);
     for (int b = tid; b < PT_BUCKETS; b += blockDim.x) tbl[b] = nspl > 0 ? tables[(i64)row * PT_BUCKETS + b] : 0;
     if (tid < P) {
         cnt[tid] = (int)mycnt;
@@ -695,8 +716,8 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
     }
     float f_first = 0.f, inv_w = 0.f;
     if (nspl > 0) {
-        f_first = splf[0];
-        const float w = (splf[nspl - 1] - f_first) * (1.0f / PT_BUCKETS);
+        f_first = splf[1];
+        const float w = (splf[nspl] - f_first) * (1.0f / PT_BUCKETS);
         if (w > 0.f && w < INFINITY) inv_w = 1.0f / w;
     }
     __syncthreads();
@@ -712,7 +733,7 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
             for (int u = 0; u < HV_UNROLL; ++u) {
                 if (c0 + (i64)u * blockDim.x >= n) break;
                 const double x = xs[u];
-                const int part = nspl > 0 ? part_of(__double2float_rn(x - x0), splf, nspl, tbl, f_first, inv_w) : 0;
+                const int part = nspl > 0 ? part_of(__double2float_rn(x - x0), splf, tbl, f_first, inv_w) : 0;
                 const int h = hidx[part];
                 if (h < 0) continue;
                 const u64 bits = (u64)__double_as_longlong(x + 0.0);  // -0.0 and +0.0 are one value
@@ -759,7 +780,7 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
             const i64 c = c0 + (i64)u * blockDim.x;
             if (c >= n) break;
             const double x = xs[u];
-            const int part = nspl > 0 ? part_of(__double2float_rn(x - x0), splf, nspl, tbl, f_first, inv_w) : 0;
+            const int part = nspl > 0 ? part_of(__double2float_rn(x - x0), splf, tbl, f_first, inv_w) : 0;
             const int h = hidx[part];
             if (h < 0) continue;
             const int k = hv_find(tab[h], (u64)__double_as_longlong(x + 0.0));
