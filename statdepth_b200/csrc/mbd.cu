@@ -14,11 +14,14 @@
 //                             groups a 4096-value chunk by part in shared memory (one shared atomic per
 //                             value, one global atomic per (CTA, part)) and copies the groups to the parts'
 //                             slot lists (fixed capacity CAP) with coalesced stores.  Equal values always
-//                             share a part, so tie runs never straddle parts.
-//   3. mbd_rank_kernel      : ONE WARP per (row, part): loads <= 512 values, maps them to a 22-bit
+//                             share a part, so tie runs never straddle parts.  A list entry is 8 bytes: the
+//                             value as a FLOAT offset from the part's lower splitter (monotone in x, resolution
+//                             2^-24 of the part's width) and the curve id.
+//   3. mbd_rank_kernel      : ONE WARP per (row, part): loads <= 512 offsets, maps them to a 22-bit
 //                             monotone key packed with the slot id, sorts the packed u32 keys in
 //                             registers with a shuffle bitonic network, resolves equal-key runs with
-//                             exact fp64 compares, and adds term(b, a) to acc[curve] with a 64-bit RED.
+//                             exact fp64 compares on the values of X (gathered through the curve ids; rare),
+//                             and adds b(b-1) + a(a-1) to raw[curve] with a 64-bit RED.
 //      mbd_rank_big_kernel  : persistent; drains the work list of parts with 513..1024 values.
 //      mbd_heavy_kernel     : parts with more than CAP values hold a few heavily repeated values (ties):
 //                             ranked from a per-part table of at most 8 distinct values, no sorting.
@@ -27,7 +30,7 @@
 //                             sort of order-preserving u64 keys + binary-search ranks.  Correct for any
 //                             finite input; slower.
 // HBM layout: X[t*ld + c] float64 (time-major rows are contiguous and streamed with coalesced
-// loads); acc int64[n]; part lists [row][part][CAP] float64 + uint32.
+// loads); raw uint64[n] -> acc int64[n] (mbd_finish_kernel); part lists [row][part][CAP] float32 + uint32.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -71,8 +74,7 @@ __device__ __forceinline__ float f32_unsortable(u32 k) {
 __device__ __forceinline__ int sp_swz(int g) { return g ^ ((g >> 5) & 31); }
 
 __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double *__restrict__ X, i64 n, i64 ld,
-                                                                   int P, int S, double *__restrict__ splitters,
-                                                                   float *__restrict__ splitters_f,
+                                                                   int P, int S, float *__restrict__ splitters_f,
                                                                    unsigned short *__restrict__ tables,
                                                                    int *__restrict__ status) {
     __shared__ u32 skey[MAX_SAMPLE];
@@ -124,9 +126,8 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
         for (int i = 0; i < 32; ++i) skey[sp_swz(wid * 1024 + lane * 32 + i)] = v[i];
     }
     __syncthreads();
-    // splitter p as a float offset from x[0] (what the partition compares) and as a double value (the
-    // range bound the rank kernel scales its keys with)
-    double *out = splitters + (i64)blockIdx.x * (P - 1);
+    // splitter p as a float offset from x[0]: what the partition compares, and the reference the part
+    // lists store their values against
     float *outf = splitters_f + (i64)blockIdx.x * (P - 1);
     const int nspl = P - 1;
     for (int p = tid + 1; p < P; p += SP_THREADS) s_splf[p - 1] = f32_unsortable(skey[sp_swz((int)(((i64)p * S) / P))]);
@@ -152,7 +153,6 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
         if (i < nspl) {
             s_splf[i] = mine[k];
             outf[i] = mine[k];
-            out[i] = x0 + (double)mine[k];
         }
     }
     __syncthreads();
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
 constexpr int PT_THREADS = SD_PT_THREADS;
 constexpr int PT_EPT = SD_PT_EPT;               // values per thread
 constexpr int PT_CHUNK = PT_THREADS * PT_EPT;   // 4096 values per CTA
-constexpr size_t PT_SMEM = (size_t)PT_CHUNK * 8 + (size_t)PT_CHUNK * 4 + (size_t)(MAX_PARTS * 3 + 4) * 4 +
+constexpr size_t PT_SMEM = (size_t)PT_CHUNK * 4 + (size_t)PT_CHUNK * 4 + (size_t)(MAX_PARTS * 3 + 4) * 4 +
                            (size_t)(PT_BUCKETS + 8) * 2 + 256;
 
 // part of a value = number of splitters <= f, f = float(x - x[0]).  Every step is monotone in x, so
@@ -231,11 +231,11 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_par
                                                                    const float *__restrict__ splitters_f,
                                                                    const unsigned short *__restrict__ tables,
                                                                    int *__restrict__ cursor, int *__restrict__ rowflag,
-                                                                   double *__restrict__ part_x,
+                                                                   float *__restrict__ part_x,
                                                                    u32 *__restrict__ part_j, i64 row_stride,
                                                                    int *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char pt_smem[];
-    double *sx = reinterpret_cast<double *>(pt_smem);                 // grouped values
+    float *sx = reinterpret_cast<float *>(pt_smem);                   // grouped values (offsets from the part's reference)
     u32 *sj = reinterpret_cast<u32 *>(sx + PT_CHUNK);                 // grouped (part << 12 | index in chunk)
     float *splf = reinterpret_cast<float *>(sj + PT_CHUNK);           // splitters of this row (float offsets)
     int *pre = reinterpret_cast<int *>(splf + MAX_PARTS + 4);         // per-part count, then exclusive prefix
@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_par
     //    position inside the CTA's group (shared-memory atomic)
     double x[PT_EPT];
     u32 tag[PT_EPT];  // part << 16 | position within (CTA, part)
+    float rel[PT_EPT];  // value as a float offset from the part's lower splitter (part 0: from the first splitter)
 #pragma unroll
     for (int u = 0; u < PT_EPT; ++u) {
         const int i = u * PT_THREADS + tid;
@@ -277,8 +278,16 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_par
     for (int u = 0; u < PT_EPT; ++u) {
         const int i = u * PT_THREADS + tid;
         tag[u] = 0xffffffffu;
+        rel[u] = 0.f;
         if (i < len) {
-            const int part = nspl > 0 ? part_of(__double2float_rn(x[u] - x0), splf, tbl, f_first, inv_w) : 0;
+            const double d = x[u] - x0;
+            int part = 0;
+            double ref = 0.0;
+            if (nspl > 0) {
+                part = part_of(__double2float_rn(d), splf, tbl, f_first, inv_w);
+                ref = (double)splf[max(part, 1)];
+            }
+            rel[u] = __double2float_rn(d - ref);  // monotone in x; 2^-24 of the part's width, not of |x - x0|
             tag[u] = ((u32)part << 16) | (u32)atomicAdd(&pre[part], 1);
         }
     }
@@ -327,14 +336,14 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_par
         if (tag[u] != 0xffffffffu) {
             const int part = (int)(tag[u] >> 16);
             const int pos = pre[part] + (int)(tag[u] & 0xffffu);
-            sx[pos] = x[u];
+            sx[pos] = rel[u];
             sj[pos] = ((u32)part << 12) | (u32)(u * PT_THREADS + tid);
         }
     }
     __syncthreads();
 
     // D. coalesced copy-out: consecutive grouped positions of one part go to consecutive slots
-    double *px = part_x + (i64)row * row_stride;
+    float *px = part_x + (i64)row * row_stride;
     u32 *pj = part_j + (i64)row * row_stride;
     for (int i = tid; i < len; i += PT_THREADS) {
         const u32 t = sj[i];
@@ -396,10 +405,11 @@ __global__ void mbd_finish_kernel(const u64 *__restrict__ raw2, i64 *__restrict_
 // position finds its run start with a max-scan over head positions; the run's last element records the run
 // length and every element that differs from the run's first value flags the run.  A run of one repeated
 // value (tie-heavy data; any length) then costs O(1) per element; only a run that mixes distinct values
-// under one key is counted pairwise.  Kept out of line: it is rare and must not cost the sort registers.
+// under one key is counted pairwise.  The part lists hold float offsets, so the EXACT values are read from
+// the row of X through the curve ids.  Kept out of line: it is rare and must not cost the sort registers.
 template <int EPL>
-__device__ __noinline__ void resolve_runs(const double *__restrict__ px, const int cnt, const u32 *skeys, u32 *sres,
-                                          u32 *sflag, const int lane) {
+__device__ __noinline__ void resolve_runs(const double *__restrict__ xrow, const u32 *__restrict__ pj, const int cnt,
+                                          const u32 *skeys, u32 *sres, u32 *sflag, const int lane) {
     const int p0 = lane * EPL;
     const u32 r_before = p0 > 0 && p0 <= cnt ? skeys[((p0 - 1) % EPL) * 32 + (p0 - 1) / EPL] >> 10 : 0xffffffffu;
     int last_head = -1;  // last run start inside this lane's chunk
@@ -431,7 +441,7 @@ __device__ __noinline__ void resolve_runs(const double *__restrict__ px, const i
         u32 mark = rn != r ? (u32)(pos + 1 - rs) : 0u;  // run length, recorded by the run's last element
         if (rs != pos) {
             const u32 k0 = skeys[(rs % EPL) * 32 + rs / EPL];
-            if (!(px[k & 1023u] == px[k0 & 1023u])) mark |= 0x80000000u;  // the run holds distinct values
+            if (!(xrow[pj[k & 1023u]] == xrow[pj[k0 & 1023u]])) mark |= 0x80000000u;  // the run holds distinct values
         }
         if (mark) atomicOr(&sflag[(rs % EPL) * 32 + rs / EPL], mark);
     }
@@ -451,9 +461,9 @@ __device__ __noinline__ void resolve_runs(const double *__restrict__ px, const i
         const int slot = (int)(k & 1023u);
         int less = 0, greater = 0;
         if (f & 0x80000000u) {  // mixed run: exact pairwise counting inside the run
-            const double xs = px[slot];
+            const double xs = xrow[pj[slot]];
             for (int m = rs; m < rs + len; ++m) {
-                const double xm = px[skeys[(m % EPL) * 32 + m / EPL] & 1023u];
+                const double xm = xrow[pj[skeys[(m % EPL) * 32 + m / EPL] & 1023u]];
                 less += xm < xs;
                 greater += xm > xs;
             }
@@ -463,54 +473,44 @@ __device__ __noinline__ void resolve_runs(const double *__restrict__ px, const i
 }
 
 // skeys / sres / sflag: this warp's shared scratch (CAP words each).
-// [lo, hi): value range of the part when it is known from the splitters (interior parts); otherwise
-// (first / last part, single-part rows) have_range is false and the range is measured.
+// px: the part's values as float offsets from its reference splitter (monotone in x; equal offsets do NOT imply
+// equal values, so everything that shares a key is resolved on the exact values).  [lo, hi): range of the
+// offsets when it is known from the splitters (interior parts); otherwise (first / last part, single-part
+// rows) have_range is false and the range is measured.
 template <int EPL, bool EXTRA>
-__device__ __forceinline__ void rank_part(const double *__restrict__ px, const u32 *__restrict__ pj, const int cnt,
-                                          const u32 base, const i64 row_global, const RankOut &o, u32 *skeys,
-                                          u32 *sres, u32 *sflag, const int lane, double lo, double hi,
-                                          const bool have_range) {
+__device__ __forceinline__ void rank_part(const float *__restrict__ px, const u32 *__restrict__ pj,
+                                          const double *__restrict__ xrow, const int cnt, const u32 base,
+                                          const i64 row_global, const RankOut &o, u32 *skeys, u32 *sres, u32 *sflag,
+                                          const int lane, float lo, float hi, const bool have_range) {
     const u32 n32 = (u32)o.n;
     if (!have_range) {
         lo = INFINITY;
         hi = -INFINITY;
 #pragma unroll 1
         for (int s = lane; s < cnt; s += 32) {
-            const double x = px[s];
-            lo = fmin(lo, x);
-            hi = fmax(hi, x);
+            const float x = px[s];
+            lo = fminf(lo, x);
+            hi = fmaxf(hi, x);
         }
-        lo = warp_min(lo);
-        hi = warp_max(hi);
-        if (lo == hi) {  // every element ties: b = everything in lower parts, a = everything in higher parts
-#pragma unroll 1
-            for (int s = lane; s < cnt; s += 32) emit_rank<EXTRA>(o, row_global, pj[s], base, n32 - base - (u32)cnt);
-            return;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
         }
     }
-    // monotone 22-bit key | slot id.  lo <= x (exactly), every step below is monotone in x.
-    const double scale = (double)KEY_MAX / (hi - lo);
-    const double x_first = EPL == 32 ? px[0] : 0.0;
-    bool all_equal = true;  // only tested for the rare > CAP/2 parts, which tie-heavy rows produce in numbers
+    // monotone 22-bit key | slot id: every step below is monotone in the offset, hence in x.  hi == lo gives
+    // scale = inf and one key for all (0 * inf = NaN converts to 0): one run, resolved exactly.
+    const float scale = (float)KEY_MAX / (hi - lo);
     u32 v[EPL];
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
         const int s = lane + 32 * k;
         u32 key = 0xffffffffu;
         if (s < cnt) {
-            const double xv = px[s];
-            if (EPL == 32) all_equal &= xv == x_first;
-            const double t = (xv - lo) * scale;
-            u32 r = (u32)__double2uint_rz(t);  // NaN (inf*0) converts to 0: still consistent, resolved by the run scan
-            r = min(r, KEY_MAX);
+            const u32 r = min((u32)__float2uint_rz((px[s] - lo) * scale), KEY_MAX);  // negative / NaN -> 0
             key = (r << 10) | (u32)s;
         }
         v[k] = key;
-    }
-    if (EPL == 32 && __all_sync(0xffffffffu, all_equal)) {  // one value class: no sort needed
-#pragma unroll 1
-        for (int s = lane; s < cnt; s += 32) emit_rank<EXTRA>(o, row_global, pj[s], base, n32 - base - (u32)cnt);
-        return;
     }
     warp_bitonic_sort<EPL, u32>(v, lane);
 
@@ -537,7 +537,7 @@ __device__ __forceinline__ void rank_part(const double *__restrict__ px, const u
             sflag[i * 32 + lane] = 0u;
         }
         __syncwarp();
-        resolve_runs<EPL>(px, cnt, skeys, sres, sflag, lane);
+        resolve_runs<EPL>(xrow, pj, cnt, skeys, sres, sflag, lane);
     }
     __syncwarp();
 #pragma unroll 1
@@ -558,9 +558,11 @@ struct RankArgs {
     const int *cursor;         // [rows][P] fill counts
     const u32 *pbase;          // [rows][P] exclusive prefix of the fill counts (#values in lower parts)
     const int *rowflag;        // [rows] bit 0: has parts with > CAP values (all-equal classes), bit 1: generic path
-    const double *splitters;   // [rows][P-1]
-    const double *part_x;      // [rows][row_stride]
-    const u32 *part_j;
+    const float *splitters_f;  // [rows][P-1] offsets from x[row][0]
+    const float *part_x;       // [rows][row_stride] offsets from the part's reference splitter
+    const u32 *part_j;         // [rows][row_stride] curve ids
+    const double *X;           // the rows of this block (exact values for run resolution)
+    i64 ld;
     i64 row_stride, row0;
     int2 *biglist;             // (row, part) of parts with more than CAP/2 values
     int *bigcount;             // [0] entries appended, [1] entries claimed
@@ -571,16 +573,17 @@ __device__ __forceinline__ void rank_one(const RankArgs &a, const RankOut &o, co
                                          const int cnt, u32 *skeys, u32 *sres, u32 *sflag, const int lane) {
     const int P = a.P;
     const u32 base = a.pbase[row * P + part];
-    // interior parts: [splitter[part-1], splitter[part]) bounds the values of the part
+    // interior parts: the offsets lie in [0, splitter[part] - splitter[part-1])
     const bool have_range = part > 0 && part < P - 1;
-    double lo = 0.0, hi = 0.0;
+    float hi = 0.f;
     if (have_range) {
-        lo = a.splitters[row * (P - 1) + part - 1];
-        hi = a.splitters[row * (P - 1) + part];
+        const float *sp = a.splitters_f + row * (P - 1);
+        hi = (float)((double)sp[part] - (double)sp[part - 1]);
     }
-    const double *px = a.part_x + row * a.row_stride + (i64)part * CAP;
+    const float *px = a.part_x + row * a.row_stride + (i64)part * CAP;
     const u32 *pj = a.part_j + row * a.row_stride + (i64)part * CAP;
-    rank_part<EPL, EXTRA>(px, pj, cnt, base, a.row0 + row, o, skeys, sres, sflag, lane, lo, hi, have_range);
+    rank_part<EPL, EXTRA>(px, pj, a.X + row * a.ld, cnt, base, a.row0 + row, o, skeys, sres, sflag, lane, 0.f, hi,
+                          have_range);
 }
 
 // One warp per (row, part) for parts of at most CAP/2 values (8 or 16 keys per lane, 56 registers);
@@ -951,27 +954,27 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         if (S > MAX_SAMPLE) S = MAX_SAMPLE;
     }
     const i64 NP = pow2ceil_int(n);
-    const i64 row_stride = (i64)P * CAP > NP ? (i64)P * CAP : NP;  // 8-byte slots per row
+    const i64 row_stride = (i64)P * CAP;  // slots per row in the part lists (4-byte offset + 4-byte curve id)
 
     // rows per block: keep the part lists within ~6 GB
-    const size_t per_row = (size_t)row_stride * 12;
+    const size_t per_row = (size_t)(row_stride > NP ? row_stride : NP) * 8;
     i64 Tc = (i64)((6ull << 30) / per_row);
     if (Tc < 1) Tc = 1;
     if (Tc > T) Tc = T;
     if (Tc > 65535) Tc = 65535;
 
-    SD_TRY(ctx->buf[BUF_PART_X].reserve((size_t)Tc * row_stride * 8));
+    // float part lists; the generic path reuses the buffer as NP sortable u64 keys per row
+    SD_TRY(ctx->buf[BUF_PART_X].reserve((size_t)Tc * (row_stride * 4 > NP * 8 ? row_stride * 4 : NP * 8)));
     SD_TRY(ctx->buf[BUF_PART_J].reserve((size_t)Tc * row_stride * 4));
     SD_TRY(ctx->buf[BUF_CURSOR].reserve((size_t)Tc * (2 * P + 1) * sizeof(int)));
-    SD_TRY(ctx->buf[BUF_SPLIT].reserve((size_t)Tc * (P > 1 ? P - 1 : 1) * (sizeof(double) + sizeof(float)) +
+    SD_TRY(ctx->buf[BUF_SPLIT].reserve((size_t)Tc * (P > 1 ? P - 1 : 1) * sizeof(float) +
                                        (size_t)Tc * PT_BUCKETS * sizeof(unsigned short)));
-    double *part_x = ctx->buf[BUF_PART_X].as<double>();
+    float *part_x = ctx->buf[BUF_PART_X].as<float>();
     u32 *part_j = ctx->buf[BUF_PART_J].as<u32>();
     int *cursor = ctx->buf[BUF_CURSOR].as<int>();
     int *rowflag = cursor + (size_t)Tc * P;
     u32 *pbase = reinterpret_cast<u32 *>(rowflag + Tc);
-    double *splitters = ctx->buf[BUF_SPLIT].as<double>();
-    float *splitters_f = reinterpret_cast<float *>(splitters + (size_t)Tc * (P > 1 ? P - 1 : 1));
+    float *splitters_f = ctx->buf[BUF_SPLIT].as<float>();
     unsigned short *tables = reinterpret_cast<unsigned short *>(splitters_f + (size_t)Tc * (P > 1 ? P - 1 : 1));
     int *fb_count = ctx->d_status + 1;
     SD_TRY(ctx->buf[BUF_WORK].reserve((size_t)Tc * P * sizeof(int2) + (size_t)n * sizeof(u64)));
@@ -1000,7 +1003,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             SD_CUDA(cudaMemsetAsync(cursor, 0, (size_t)Tc * (P + 1) * sizeof(int), st));
             if (P > 1) {
                 SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SPLITTERS));
-                mbd_splitters_kernel<<<(unsigned)rows, SP_THREADS, 0, st>>>(Xb, n, ld, P, S, splitters, splitters_f,
+                mbd_splitters_kernel<<<(unsigned)rows, SP_THREADS, 0, st>>>(Xb, n, ld, P, S, splitters_f,
                                                                             tables, ctx->d_status);
                 SD_TRY(prof_end(ctx));
                 ctx->last.launches++;
@@ -1021,7 +1024,9 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             ra.cursor = cursor;
             ra.pbase = pbase;
             ra.rowflag = rowflag;
-            ra.splitters = splitters;
+            ra.splitters_f = splitters_f;
+            ra.X = Xb;
+            ra.ld = ld;
             ra.part_x = part_x;
             ra.part_j = part_j;
             ra.row_stride = row_stride;
@@ -1043,7 +1048,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         }
         // rows flagged as overflowing (or all rows when forced): generic path; idle CTAs exit at once
         SD_TRY(prof_begin(ctx, SD_PHASE_MBD_GENERIC));
-        mbd_fallback_kernel<<<(unsigned)rows, 1024, 0, st>>>(Xb, n, ld, NP, rowflag, (u64 *)part_x, row_stride, r0, o,
+        mbd_fallback_kernel<<<(unsigned)rows, 1024, 0, st>>>(Xb, n, ld, NP, rowflag, (u64 *)part_x, NP, r0, o,
                                                              ctx->d_status, fb_count);
         SD_TRY(prof_end(ctx));
         ctx->last.launches++;
