@@ -211,19 +211,25 @@ __device__ __forceinline__ void fill_splitters(float *sp, const float *__restric
     }
 }
 
+// `lower` receives sp[part], the splitter below the part (NaN for part 0).
 __device__ __forceinline__ int part_of(const float f, const float *__restrict__ sp, const unsigned short *__restrict__ tbl,
-                                       const float f_first, const float inv_w) {
+                                       const float f_first, const float inv_w, float &lower) {
     float fb = (f - f_first) * inv_w;
     fb = fminf(fmaxf(fb, 0.f), (float)(PT_BUCKETS - 1));  // also maps NaN (inf * 0) to 0
     int idx = tbl[(int)fb];
     const float below = sp[idx], s0 = sp[idx + 1], s1 = sp[idx + 2];
     if (below > f) {  // guess too high (bucket rounding): rare
         do --idx; while (sp[idx] > f);
+        lower = sp[idx];
         return idx;
     }
-    idx += (int)(s0 <= f) + (int)(s1 <= f);
-    if (s1 <= f)  // more than two splitters of this bucket are <= f: rare
+    const bool ge0 = s0 <= f, ge1 = s1 <= f;
+    idx += (int)ge0 + (int)ge1;
+    lower = ge1 ? s1 : (ge0 ? s0 : below);
+    if (ge1) {  // more than two splitters of this bucket are <= f: rare
         while (sp[idx + 1] <= f) ++idx;
+        lower = sp[idx];
+    }
     return idx;
 }
 
@@ -284,8 +290,9 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_par
             int part = 0;
             double ref = 0.0;
             if (nspl > 0) {
-                part = part_of(__double2float_rn(d), splf, tbl, f_first, inv_w);
-                ref = (double)splf[max(part, 1)];
+                float lower;
+                part = part_of(__double2float_rn(d), splf, tbl, f_first, inv_w, lower);
+                ref = (double)(part > 0 ? lower : f_first);
             }
             rel[u] = __double2float_rn(d - ref);  // monotone in x; 2^-24 of the part's width, not of |x - x0|
             tag[u] = ((u32)part << 16) | (u32)atomicAdd(&pre[part], 1);
@@ -736,7 +743,8 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
             for (int u = 0; u < HV_UNROLL; ++u) {
                 if (c0 + (i64)u * blockDim.x >= n) break;
                 const double x = xs[u];
-                const int part = nspl > 0 ? part_of(__double2float_rn(x - x0), splf, tbl, f_first, inv_w) : 0;
+                float lower;
+                const int part = nspl > 0 ? part_of(__double2float_rn(x - x0), splf, tbl, f_first, inv_w, lower) : 0;
                 const int h = hidx[part];
                 if (h < 0) continue;
                 const u64 bits = (u64)__double_as_longlong(x + 0.0);  // -0.0 and +0.0 are one value
@@ -783,7 +791,8 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
             const i64 c = c0 + (i64)u * blockDim.x;
             if (c >= n) break;
             const double x = xs[u];
-            const int part = nspl > 0 ? part_of(__double2float_rn(x - x0), splf, tbl, f_first, inv_w) : 0;
+            float lower;
+                const int part = nspl > 0 ? part_of(__double2float_rn(x - x0), splf, tbl, f_first, inv_w, lower) : 0;
             const int h = hidx[part];
             if (h < 0) continue;
             const int k = hv_find(tab[h], (u64)__double_as_longlong(x + 0.0));
