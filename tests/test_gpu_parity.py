@@ -35,7 +35,8 @@ def test_mbd_counts_bit_exact(engine, oracle, T, n, seed):
     assert engine.timings()["fallback_rows"] == 0  # well-spread data never needs the generic path
 
 
-@pytest.mark.parametrize("maker", ["round", "few", "constant", "half_constant", "outliers", "sorted", "negzero"])
+@pytest.mark.parametrize("maker", ["round", "few", "constant", "half_constant", "outliers", "sorted", "negzero",
+                                   "far_reference"])
 def test_mbd_ties_and_skew(engine, oracle, maker):
     rng = np.random.default_rng(11)
     T, n = 24, 6000
@@ -55,6 +56,8 @@ def test_mbd_ties_and_skew(engine, oracle, maker):
         X = np.sort(X, axis=1)
     elif maker == "negzero":
         X = np.where(rng.random((T, n)) < 0.5, 0.0, -0.0)
+    elif maker == "far_reference":  # column 0 is the offsets' reference: every float offset collapses to one value
+        X[:, 0] = 1e13
     got = engine.band_depth_counts(X, None, 2, True)
     assert (got == oracle.mbd_counts_all(X)).all()
 
@@ -153,6 +156,59 @@ def test_mbd_full_size_properties(engine, oracle):
     Xa = X[:4].copy()
     Xa[:, :3000] = Xa[:, [3000]] + np.arange(3000) * 1e-13
     assert (engine.band_depth_counts(Xa, None, 2, True) == oracle.mbd_counts_all(Xa)).all()
+
+
+def _random_matrix(rng, T, n):
+    """Random shapes of trouble: continuous, rounded, few classes, constant rows, point masses, tiny spreads."""
+    kind = rng.integers(0, 7)
+    X = rng.standard_normal((T, n)).cumsum(0)
+    if kind == 1:
+        X = np.round(X * rng.choice([0.2, 1.0, 5.0]))
+    elif kind == 2:
+        X = rng.integers(0, int(rng.integers(1, 6)), size=(T, n)).astype(np.float64)
+    elif kind == 3:
+        X[rng.integers(0, T)] = 7.0
+    elif kind == 4:  # zero-inflated
+        X[rng.random((T, n)) < rng.choice([0.1, 0.5, 0.9])] = 0.0
+    elif kind == 5:  # spreads far below the magnitude: float offsets collapse, exact compares must decide
+        X = 1e6 + X * 1e-9
+    elif kind == 6:  # a few huge outliers stretch the first / last part
+        X[:, rng.integers(0, n, size=3)] *= 1e200
+    return X
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_mbd_randomized_differential(engine, oracle, seed):
+    """Seeded random shapes, tie structures and query subsets: counts (j = 2, 3) and ranks equal the oracle's."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([3, 17, 200, 1024, 1025, 1500, 4000, 9000, 20_000]))
+    T = int(rng.integers(1, 12))
+    X = _random_matrix(rng, T, n)
+    want2, wb, wa = oracle.mbd_counts_all(X, j=2, want_ranks=True)
+    assert (engine.band_depth_counts(X, None, 2, True) == want2).all()
+    assert (engine.band_depth_counts(X, None, 3, True) == oracle.mbd_counts_all(X, j=3)).all()
+    below, above = engine.band_ranks(X)
+    assert (below == wb).all() and (above == wa).all()
+    q = rng.choice(n, size=min(n, 5), replace=False)
+    assert (engine.band_depth_counts(X, q, 2, True) == want2[q]).all()
+    assert (engine.band_depth_counts(np.asfortranarray(X), q, 2, True) == want2[q]).all()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_bd_randomized_differential(engine, oracle, seed):
+    """Strict band depth: every implementation against the oracle on random shapes with and without ties."""
+    from statdepth_b200._engine import BD_AUTO, BD_BITS, BD_GEMM, BD_MATCH, OPT_BD_IMPL
+    rng = np.random.default_rng(2000 + seed)
+    n = int(rng.choice([3, 9, 64, 130, 300, 700]))
+    T = int(rng.choice([1, 5, 31, 32, 33, 100]))
+    X = _random_matrix(rng, T, n)
+    want = oracle.bd_counts(X)
+    try:
+        for impl in (BD_AUTO, BD_BITS, BD_GEMM, BD_MATCH):
+            engine.set_option(OPT_BD_IMPL, impl)
+            assert (engine.band_depth_counts(X, None, 2, False) == want).all(), impl
+    finally:
+        engine.set_option(OPT_BD_IMPL, BD_AUTO)
 
 
 def test_mbd_heavy_parts_edge_cases(engine, oracle):
