@@ -7,7 +7,7 @@
 // so the whole relaxed numerator is a per-row ranking problem (kernel "K1").
 //
 // Pipeline per block of time rows (all kernels on ctx->stream, no host sync):
-//   1. mbd_splitters_kernel : one CTA per row sorts a strided sample (u32 images of float(x - x[0]), register
+//   1. mbd_splitters_kernel : one CTA per row sorts a strided sample (u32 images of float(x - ref), register
 //                             bitonic network per warp + swizzled shared-memory merges) and emits P-1
 //                             equal-mass splitters.
 //   2. mbd_partition_kernel : streams the row once from HBM, finds each value's part with a bucket table,
@@ -56,13 +56,21 @@ __device__ __forceinline__ i64 comb3_dev(i64 m) {
 
 // ---------------------------------------------------------------------------------------------
 // 1. splitters: one CTA per row sorts a strided sample of S = 1024*W values (W = 1, 2, 4 or 8 warps)
-//    as order-preserving u32 images of float(x - x[0]) -- splitters need not be data values, any
+//    as order-preserving u32 images of float(x - ref) -- splitters need not be data values, any
 //    non-decreasing sequence works, and 32-bit keys sort on registers at 2 instructions per
 //    compare-exchange.  Each warp sorts 1024 keys (EPL = 32); the 1..3 remaining merge levels exchange
 //    partners through XOR-swizzled shared memory and finish on registers.  v1 (fp64 bitonic in shared
 //    memory, 91 block-wide stages) took 0.56 ms of a 3.6 ms step.
 // ---------------------------------------------------------------------------------------------
 constexpr int SP_THREADS = 256;
+
+// Reference value of a row: splitters and part lists work on float(x - reference), so the reference has to
+// sit inside the bulk of the row or the float offsets lose the differences between values.  The median of
+// three entries survives one outlier; every kernel recomputes it the same way.
+__device__ __forceinline__ double row_reference(const double *__restrict__ xr, const i64 n) {
+    const double a = xr[0], b = xr[n >> 1], c = xr[n - 1];
+    return fmax(fmin(a, b), fmin(fmax(a, b), c));
+}
 
 __device__ __forceinline__ u32 f32_sortable(float f) {
     const u32 b = __float_as_uint(f);
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int W = S >> 10;  // warps that hold samples
     const double *xr = X + (i64)blockIdx.x * ld;
-    const double x0 = xr[0];
+    const double x0 = row_reference(xr, n);
     u32 v[32];
     if (wid < W) {
         bool bad = false;
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
         for (int i = 0; i < 32; ++i) skey[sp_swz(wid * 1024 + lane * 32 + i)] = v[i];
     }
     __syncthreads();
-    // splitter p as a float offset from x[0]: what the partition compares, and the reference the part
+    // splitter p as a float offset from the row reference: what the partition compares, and the reference the part
     // lists store their values against
     float *outf = splitters_f + (i64)blockIdx.x * (P - 1);
     const int nspl = P - 1;
@@ -194,7 +202,7 @@ constexpr int PT_CHUNK = PT_THREADS * PT_EPT;   // 4096 values per CTA
 constexpr size_t PT_SMEM = (size_t)PT_CHUNK * 4 + (size_t)PT_CHUNK * 4 + (size_t)(MAX_PARTS * 3 + 4) * 4 +
                            (size_t)(PT_BUCKETS + 8) * 2 + 256;
 
-// part of a value = number of splitters <= f, f = float(x - x[0]).  Every step is monotone in x, so
+// part of a value = number of splitters <= f, f = float(x - ref).  Every step is monotone in x, so
 // equal values share a part and parts are ordered.  sp[] is the row's splitter list padded with sentinels:
 // sp[0] = NaN, sp[1 + i] = splitter i, sp[nspl + 1] = sp[nspl + 2] = NaN (every compare with a sentinel is
 // false, also for f = +-inf, so the scans stop at the ends).  The lookup table only provides
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_par
         const int i = u * PT_THREADS + tid;
         x[u] = i < len ? xr[c0 + i] : 0.0;
     }
-    const double x0 = xr[0];
+    const double x0 = row_reference(xr, n);
     fill_splitters(splf, splitters_f + (i64)row * nspl, nspl, tid, PT_THREADS);
     for (int i = tid; i < P; i += PT_THREADS) pre[i] = 0;
     for (int b = tid; b < PT_BUCKETS; b += PT_THREADS) tbl[b] = nspl > 0 ? tables[(i64)row * PT_BUCKETS + b] : 0;
@@ -565,7 +573,7 @@ struct RankArgs {
     const int *cursor;         // [rows][P] fill counts
     const u32 *pbase;          // [rows][P] exclusive prefix of the fill counts (#values in lower parts)
     const int *rowflag;        // [rows] bit 0: has parts with > CAP values (all-equal classes), bit 1: generic path
-    const float *splitters_f;  // [rows][P-1] offsets from x[row][0]
+    const float *splitters_f;  // [rows][P-1] offsets from the row's reference
     const float *part_x;       // [rows][row_stride] offsets from the part's reference splitter
     const u32 *part_j;         // [rows][row_stride] curve ids
     const double *X;           // the rows of this block (exact values for run resolution)
@@ -700,7 +708,7 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
     if ((rowflag[row] & 3) != 1) return;  // no heavy part, or already generic
     const int nspl = P - 1;
     const double *xr = X + (i64)row * ld;
-    const double x0 = xr[0];
+    const double x0 = row_reference(xr, n);
     fill_splitters(splf, splitters_f + (i64)row * nspl, nspl, tid, blockDim.x);
     for (int b = tid; b < PT_BUCKETS; b += blockDim.x) tbl[b] = nspl > 0 ? tables[(i64)row * PT_BUCKETS + b] : 0;
     if (tid < P) {

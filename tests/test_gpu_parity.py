@@ -56,8 +56,10 @@ def test_mbd_ties_and_skew(engine, oracle, maker):
         X = np.sort(X, axis=1)
     elif maker == "negzero":
         X = np.where(rng.random((T, n)) < 0.5, 0.0, -0.0)
-    elif maker == "far_reference":  # column 0 is the offsets' reference: every float offset collapses to one value
+    elif maker == "far_reference":  # outliers where the offsets' reference is taken from (first / middle / last)
         X[:, 0] = 1e13
+        X[::2, n - 1] = -1e13
+        X += 1e7
     got = engine.band_depth_counts(X, None, 2, True)
     assert (got == oracle.mbd_counts_all(X)).all()
 
