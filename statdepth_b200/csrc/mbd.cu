@@ -487,6 +487,8 @@ __device__ __noinline__ void resolve_runs(const double *__restrict__ xrow, const
     }
 }
 
+constexpr int EMIT_DEPTH = 4;
+
 // skeys / sres / sflag: this warp's shared scratch (CAP words each).
 // px: the part's values as float offsets from its reference splitter (monotone in x; equal offsets do NOT imply
 // equal values, so everything that shares a key is resolved on the exact values).  [lo, hi): range of the
@@ -555,10 +557,21 @@ __device__ __forceinline__ void rank_part(const float *__restrict__ px, const u3
         resolve_runs<EPL>(xrow, pj, cnt, skeys, sres, sflag, lane);
     }
     __syncwarp();
+    // emission in slot order (coalesced curve ids); EMIT_DEPTH ids are in flight per step, because the RED's address
+    // waits for its id and a one-at-a-time loop spent 40 % of the kernel's stall samples right here
 #pragma unroll 1
-    for (int s = lane; s < cnt; s += 32) {
-        const u32 res = sres[s];
-        emit_rank<EXTRA>(o, row_global, pj[s], base + (res & 0xffffu), n32 - base - (res >> 16));
+    for (int s0 = lane; s0 < cnt; s0 += 32 * EMIT_DEPTH) {
+        u32 j[EMIT_DEPTH], res[EMIT_DEPTH];
+#pragma unroll
+        for (int u = 0; u < EMIT_DEPTH; ++u) {
+            const int s = s0 + 32 * u;
+            j[u] = s < cnt ? pj[s] : 0u;
+            res[u] = s < cnt ? sres[s] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < EMIT_DEPTH; ++u)
+            if (s0 + 32 * u < cnt)
+                emit_rank<EXTRA>(o, row_global, j[u], base + (res[u] & 0xffffu), n32 - base - (res[u] >> 16));
     }
     __syncwarp();
 }
