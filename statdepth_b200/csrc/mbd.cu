@@ -518,6 +518,9 @@ __device__ __forceinline__ void rank_part(const float *__restrict__ px, const u3
     // monotone 22-bit key | slot id: every step below is monotone in the offset, hence in x.  hi == lo gives
     // scale = inf and one key for all (0 * inf = NaN converts to 0): one run, resolved exactly.
     const float scale = (float)KEY_MAX / (hi - lo);
+    u32 jnext[EMIT_DEPTH];  // curve ids of the first emission group, fetched under the sort
+#pragma unroll
+    for (int u = 0; u < EMIT_DEPTH; ++u) jnext[u] = lane + 32 * u < cnt ? pj[lane + 32 * u] : 0u;
     u32 v[EPL];
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
@@ -557,16 +560,19 @@ __device__ __forceinline__ void rank_part(const float *__restrict__ px, const u3
         resolve_runs<EPL>(xrow, pj, cnt, skeys, sres, sflag, lane);
     }
     __syncwarp();
-    // emission in slot order (coalesced curve ids); EMIT_DEPTH ids are in flight per step, because the RED's address
-    // waits for its id and a one-at-a-time loop spent 40 % of the kernel's stall samples right here
+    // emission in slot order (coalesced curve ids).  The RED's address waits for its id: a one-at-a-time loop
+    // spent 40 % of the kernel's stall samples here, so EMIT_DEPTH ids are fetched a step ahead (the first
+    // group before the sort).
 #pragma unroll 1
     for (int s0 = lane; s0 < cnt; s0 += 32 * EMIT_DEPTH) {
         u32 j[EMIT_DEPTH], res[EMIT_DEPTH];
 #pragma unroll
         for (int u = 0; u < EMIT_DEPTH; ++u) {
+            j[u] = jnext[u];
             const int s = s0 + 32 * u;
-            j[u] = s < cnt ? pj[s] : 0u;
             res[u] = s < cnt ? sres[s] : 0u;
+            const int sn = s + 32 * EMIT_DEPTH;
+            jnext[u] = sn < cnt ? pj[sn] : 0u;
         }
 #pragma unroll
         for (int u = 0; u < EMIT_DEPTH; ++u)
