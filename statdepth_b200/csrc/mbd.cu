@@ -96,11 +96,11 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
         bool bad = false;
         // strided sample taken in quads of 4 consecutive values (one 32 B sector each)
         const i64 nquad = n >> 2;
-        const int squad = S >> 2;
+        const int squad_shift = __ffs(S >> 2) - 1;  // S is a power of two
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const int g = wid * 1024 + lane * 32 + i;
-            const i64 idx = (((i64)(g >> 2) * nquad) / squad) * 4 + (g & 3);
+            const i64 idx = (((i64)(g >> 2) * nquad) >> squad_shift) * 4 + (g & 3);
             const double x = xr[idx];
             bad |= !isfinite(x);
             v[i] = f32_sortable(__double2float_rn(x - x0));
