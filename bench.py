@@ -321,16 +321,21 @@ def main():
     kern_s = kern_ns / 1e9 / args.steps
     achieved = alg_bytes / kern_s / 1e9
     dominant = max(phases, key=phases.get) if phases else None
-    # DRAM traffic of one step: ncu --set full (profiles/ncu_r01_final_summary.md) measured 405 MB for a
-    # 128-row block of 100k curves (sample read + one HBM round trip of the part lists) = 3.95 bytes per
-    # algorithmic byte; scaled to this rank's rows.  null for other shapes.
-    traffic = 3.95 * alg_bytes_placeholder if n == 100_000 else None
+    # DRAM traffic of one step: ncu --set full on the full cfg2 step (profiles/ncu_r01_v12_summary.md) measured
+    # 276 MB (splitters) + 1 619 MB (partition) + 796 MB (rank) + ~75 MB (big parts, finish) = 2 766 MB
+    # (sample read + one HBM round trip of the 8-byte part-list entries) = 3.37 bytes per algorithmic byte;
+    # scaled to this rank's rows.  null for other shapes.
+    traffic = 3.37 * alg_bytes_placeholder if n == 100_000 else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, round-1 capture, scaled by rows",
+            "traffic": traffic, "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per kernel, round-1 v12 capture, scaled by rows",
             "peak_source": peak_src,
             "kernel": "all kernels of one step (per-rank); dominant phase: %s" % dominant,
             "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": kern_s * 1e3,
             "phase_ms_per_step": {k: v / 1e6 / args.steps for k, v in phases.items()}}
+    if dominant:  # the same algorithmic bytes over the dominant phase alone
+        dom_s = phases[dominant] / 1e9 / args.steps
+        roof["dominant_phase"] = {"name": dominant, "ms_per_step": dom_s * 1e3, "achieved": alg_bytes / dom_s / 1e9,
+                                  "frac": alg_bytes / dom_s / 1e9 / peak}
     if not relax:
         # strict BD: int8-tensor-equivalent dense work 2*(2T)*C(n-1,2) ops per depth-eval
         ops = 2.0 * (2 * T) * comb(n - 1, 2) * nq_local
