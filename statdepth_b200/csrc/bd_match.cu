@@ -7,7 +7,7 @@
 // EXACTLY  B_o2 == A_o1: the two sign vectors are complements.  So for the tie-free curves F
 //     #pairs in F x F  =  1/2 * sum_{o in F} #{o' in F : B_o' == A_o}
 // which is a dictionary lookup, not a pair enumeration:
-//   bd_sig_kernel   : sign words (natural time order), a 64-bit hash of B_o and of its complement, and a
+//   bd_sig_kernel   : sign words (one fixed bit order), a 64-bit hash of B_o and of its complement, and a
 //                     tie-free flag per (query, other curve); 8 queries per thread.
 //   bd_match_kernel : one CTA per query sorts the (hash | curve id) keys of the tie-free curves (register
 //                     bitonic network on u64 + swizzled shared-memory merges), checks that every run of
@@ -43,7 +43,7 @@ __device__ __forceinline__ u64 bm_final(u64 h) {
     return h;
 }
 
-// Mw[(q*W + w)*m + o] = {below, above} bits of time points 32w .. 32w+31 (natural order);
+// Mw[(q*W + w)*m + o] = {below, above} bits of time points 32w .. 32w+31 (first time point in the highest used bit);
 // sig[q*m + o] = {hash(B), hash(~B & valid)};  tf[q*m + o] = 1 iff o never ties with q.
 __global__ void __launch_bounds__(128) bd_sig_kernel(const double *__restrict__ X, const i64 T, const i64 n,
                                                      const i64 ld, const i64 *__restrict__ qidx, const int nqb,
@@ -80,15 +80,18 @@ __global__ void __launch_bounds__(128) bd_sig_kernel(const double *__restrict__ 
 #pragma unroll
         for (int qq = 0; qq < BM_SQ; ++qq) b[qq] = a[qq] = 0u;
         const double *col = X + (i64)w * 32 * ld + c;
-#pragma unroll 4
+#pragma unroll 8
         for (int tt = 0; tt < tmax; ++tt) {
             const double x = col[(i64)tt * ld];
             bad |= !isfinite(x);
 #pragma unroll
             for (int qq = 0; qq < BM_SQ; ++qq) {
+                // shift-in as 2*w + bit: a multiply-add (FMA pipe) instead of shift + or on the ALU pipe, which
+                // this kernel keeps 78 % busy.  Time point tt lands in bit tmax-1-tt of the word: any fixed bit
+                // order serves (words are only compared with, and ANDed against, words built the same way).
                 const double xq = sq[tt][qq];
-                b[qq] |= (u32)(x < xq) << tt;
-                a[qq] |= (u32)(x > xq) << tt;
+                b[qq] = b[qq] * 2u + (u32)(x < xq);
+                a[qq] = a[qq] * 2u + (u32)(x > xq);
             }
         }
 #pragma unroll
