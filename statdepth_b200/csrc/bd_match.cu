@@ -7,8 +7,10 @@
 // EXACTLY  B_o2 == A_o1: the two sign vectors are complements.  So for the tie-free curves F
 //     #pairs in F x F  =  1/2 * sum_{o in F} #{o' in F : B_o' == A_o}
 // which is a dictionary lookup, not a pair enumeration:
-//   bd_sig_kernel   : sign words (one fixed bit order), a 64-bit hash of B_o and of its complement, and a
-//                     tie-free flag per (query, other curve); 8 queries per thread.
+//   bd_sig_rank_kernel : sign words (one fixed bit order), a 64-bit hash of B_o and of its complement, and a
+//                     tie-free flag per (query, other curve); 8 queries per thread.  Works on the per-time-point
+//                     RANKS of the curves (one pass of the mbd.cu rank pipeline), two 15-bit compares per
+//                     32-bit subtraction.  bd_sig_kernel is the float64 variant for few queries / long series.
 //   bd_match_kernel : one CTA per query sorts the (hash | curve id) keys of the tie-free curves (register
 //                     bitonic network on u64 + swizzled shared-memory merges), checks that every run of
 //                     equal hashes holds ONE sign vector (word-by-word), looks every curve's complement up by
@@ -116,6 +118,97 @@ __global__ void __launch_bounds__(128) bd_sig_kernel(const double *__restrict__ 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Signatures from RANKS.  At one time point "x_o < x_q" is "rank_o < rank_q" when rank = number of curves
+// strictly below (ties share a rank), so the per-row rank pipeline of mbd.cu turns the float64 compares of
+// every (query, curve, time point) into 15-bit integer compares, two per 32-bit subtraction:
+//     (r2 | 0x80008000) - q2  has bit 15 / 31 set  iff  r >= q  in the low / high half (no borrow between halves),
+// and likewise for q >= r.  ~4 warp instructions per 32 comparisons instead of ~11 with DSETP + predicate-to-bit.
+// Word layout (any fixed order serves): bit k <-> time point 32w + 2k, bit 16 + k <-> time point 32w + 2k + 1.
+// ---------------------------------------------------------------------------------------------
+constexpr u32 BM_GUARD = 0x80008000u;
+
+// Rp[tp*n + c] = rank[2tp][c] | rank[2tp+1][c] << 16; time points past T get rank 0 for everybody (a tie)
+__global__ void bd_pack_ranks_kernel(const int *__restrict__ rank_b, const i64 T, const i64 n, const i64 TP,
+                                     u32 *__restrict__ Rp) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= TP * n) return;
+    const i64 tp = i / n, c = i - tp * n;
+    const i64 t0 = 2 * tp, t1 = t0 + 1;
+    const u32 lo = t0 < T ? (u32)rank_b[t0 * n + c] : 0u;
+    const u32 hi = t1 < T ? (u32)rank_b[t1 * n + c] : 0u;
+    Rp[i] = lo | (hi << 16);
+}
+
+__global__ void __launch_bounds__(128) bd_sig_rank_kernel(const u32 *__restrict__ Rp, const i64 T, const i64 n,
+                                                          const i64 *__restrict__ qidx, const int nqb, const int W,
+                                                          uint2 *__restrict__ Mw, ulonglong2 *__restrict__ sig,
+                                                          unsigned char *__restrict__ tf) {
+    __shared__ u32 sq[16][BM_SQ];
+    __shared__ i64 sqi[BM_SQ];
+    const int q0 = blockIdx.y * BM_SQ;
+    if (threadIdx.x < BM_SQ) sqi[threadIdx.x] = q0 + threadIdx.x < nqb ? qidx[q0 + threadIdx.x] : -1;
+    const i64 m = n - 1;
+    const i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per CURVE, BM_SQ queries each
+    const bool live = c < n;
+    u64 hb[BM_SQ], hc[BM_SQ];
+    bool tiefree[BM_SQ];
+#pragma unroll
+    for (int qq = 0; qq < BM_SQ; ++qq) {
+        hb[qq] = hc[qq] = 0x243F6A8885A308D3ull;
+        tiefree[qq] = true;
+    }
+    for (int w = 0; w < W; ++w) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 16 * BM_SQ; i += blockDim.x) {
+            const int k = i / BM_SQ, qq = i % BM_SQ;
+            sq[k][qq] = sqi[qq] >= 0 ? Rp[((i64)w * 16 + k) * n + sqi[qq]] : 0u;
+        }
+        __syncthreads();
+        if (!live) continue;
+        const i64 rem = T - (i64)w * 32;  // >= 1
+        const int n_even = rem >= 31 ? 16 : (int)((rem + 1) >> 1), n_odd = rem >= 32 ? 16 : (int)(rem >> 1);
+        const u32 valid = ((1u << n_even) - 1u) | (((1u << n_odd) - 1u) << 16);
+        const u32 *col = Rp + (i64)w * 16 * n + c;
+        u32 r2[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r2[k] = col[(i64)k * n];
+        u32 ge[BM_SQ], le[BM_SQ];
+#pragma unroll
+        for (int qq = 0; qq < BM_SQ; ++qq) ge[qq] = le[qq] = 0u;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const u32 rg = r2[k] | BM_GUARD;
+#pragma unroll
+            for (int qq = 0; qq < BM_SQ; ++qq) {
+                const u32 q2 = sq[k][qq];
+                ge[qq] = (ge[qq] >> 1) | ((rg - q2) & BM_GUARD);
+                le[qq] = (le[qq] >> 1) | (((q2 | BM_GUARD) - r2[k]) & BM_GUARD);
+            }
+        }
+#pragma unroll
+        for (int qq = 0; qq < BM_SQ; ++qq) {
+            const u32 b = ~ge[qq] & valid, a = ~le[qq] & valid;
+            const i64 qi = sqi[qq];
+            if (qi >= 0 && c != qi) Mw[((i64)(q0 + qq) * W + w) * m + (c - (c > qi))] = make_uint2(b, a);
+            hb[qq] = bm_mix(hb[qq], b);
+            hc[qq] = bm_mix(hc[qq], ~b & valid);
+            tiefree[qq] = tiefree[qq] && ((b | a) == valid);
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int qq = 0; qq < BM_SQ; ++qq) {
+        const i64 qi = sqi[qq];
+        if (qi >= 0 && c != qi) {
+            const i64 o = c - (c > qi);
+            sig[(i64)(q0 + qq) * m + o] = make_ulonglong2(bm_final(hb[qq]), bm_final(hc[qq]));
+            tf[(i64)(q0 + qq) * m + o] = tiefree[qq] ? 1 : 0;
+        }
+    }
+}
+
 __device__ __forceinline__ int bm_swz(int g) { return g ^ ((g >> 4) & 15); }
 
 // 51-bit hash field of a key; the all-ones value is reserved for the sentinel (sorts last)
@@ -131,14 +224,12 @@ __device__ __forceinline__ bool bm_same_b(const uint2 *__restrict__ Mq, const in
         if (Mq[(i64)w * m + o].x != Mq[(i64)w * m + p].x) return false;
     return true;
 }
-// complement of o's B words (within the valid bits) equals p's B words?
-__device__ __forceinline__ bool bm_complement(const uint2 *__restrict__ Mq, const int W, const i64 m, const i64 T,
-                                              const int o, const int p) {
-    for (int w = 0; w < W; ++w) {
-        const int tmax = (T - (i64)w * 32) < 32 ? (int)(T - (i64)w * 32) : 32;
-        const u32 valid = tmax == 32 ? 0xffffffffu : ((1u << tmax) - 1u);
-        if ((~Mq[(i64)w * m + o].x & valid) != Mq[(i64)w * m + p].x) return false;
-    }
+// complement of o's B words equals p's B words?  o is tie-free, so its A words ARE that complement (within the
+// valid bits, whatever the bit order of the words).
+__device__ __forceinline__ bool bm_complement(const uint2 *__restrict__ Mq, const int W, const i64 m, const int o,
+                                              const int p) {
+    for (int w = 0; w < W; ++w)
+        if (Mq[(i64)w * m + o].y != Mq[(i64)w * m + p].x) return false;
     return true;
 }
 
@@ -222,7 +313,7 @@ __global__ void __launch_bounds__(BM_THREADS) bd_match_kernel(const uint2 *__res
         }
         if (lo < nF && (skey[bm_swz(lo)] >> 13) == target) {
             const int rep = (int)(skey[bm_swz(lo)] & BM_IDMASK);
-            if (bm_complement(Mq, W, m, T, o, rep)) {
+            if (bm_complement(Mq, W, m, o, rep)) {
                 int l2 = lo, h2 = nF;  // first position with hash > target
                 while (l2 < h2) {
                     const int mid = (l2 + h2) >> 1;
@@ -303,20 +394,40 @@ int bd_strict_match_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, 
     if (QB < BM_SQ) QB = BM_SQ;
     if (QB > 32768) QB = 32768;
     if (QB > nq) QB = nq;
+    const size_t smem = (size_t)BM_MAXM * sizeof(u64);
+    SD_CUDA(cudaFuncSetAttribute(bd_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // ranks of all curves at every time point (one pass of the rank pipeline), packed in pairs for the signature
+    // kernel; very long series keep the float64 signature kernel (the rank matrix would not pay)
+    const i64 TP = W * 16;
+    const bool by_ranks = T * n <= (1ll << 26) && nq >= 64;
+    u32 *Rp = nullptr;
+    if (by_ranks) {
+        SD_TRY(ctx->buf[BUF_RANKS].reserve((size_t)T * n * sizeof(int) + (size_t)TP * n * sizeof(u32) +
+                                           (size_t)n * sizeof(i64)));
+        i64 *acc = ctx->buf[BUF_RANKS].as<i64>();  // 8-byte items first: the 4-byte arrays may have odd lengths
+        int *rank_b = reinterpret_cast<int *>(acc + n);
+        Rp = reinterpret_cast<u32 *>(rank_b + (size_t)T * n);
+        SD_TRY(mbd_all_device(ctx, dX, T, n, ld, false, acc, nullptr, rank_b, nullptr));
+        SD_TRY(prof_begin(ctx, SD_PHASE_BD_MASKS));
+        bd_pack_ranks_kernel<<<(unsigned)ceil_div(TP * n, 256), 256, 0, st>>>(rank_b, T, n, TP, Rp);
+        SD_TRY(prof_end(ctx));
+        ctx->last.launches++;
+    }
+    // signature / flag storage borrows rank-pipeline buffers (after the rank pass, stream ordered)
     SD_TRY(ctx->buf[BUF_MASK].reserve((size_t)QB * W * m * sizeof(uint2)));
-    // signature / flag storage borrows rank-pipeline buffers: the strict path never runs that pipeline
     SD_TRY(ctx->buf[BUF_PART_X].reserve((size_t)QB * m * sizeof(ulonglong2) + (size_t)QB * m + (size_t)nq + 64));
     uint2 *Mw = ctx->buf[BUF_MASK].as<uint2>();
     ulonglong2 *sig = ctx->buf[BUF_PART_X].as<ulonglong2>();
     unsigned char *tf = reinterpret_cast<unsigned char *>(sig + (size_t)QB * m);
     unsigned char *flag = tf + (size_t)QB * m;  // nq flags
-    const size_t smem = (size_t)BM_MAXM * sizeof(u64);
-    SD_CUDA(cudaFuncSetAttribute(bd_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (i64 q0 = 0; q0 < nq; q0 += QB) {
         const int nqb = (int)(nq - q0 < QB ? nq - q0 : QB);
+        const dim3 sgrid((unsigned)ceil_div(n, 128), (unsigned)ceil_div(nqb, BM_SQ));
         SD_TRY(prof_begin(ctx, SD_PHASE_BD_MASKS));
-        bd_sig_kernel<<<dim3((unsigned)ceil_div(n, 128), (unsigned)ceil_div(nqb, BM_SQ)), 128, 0, st>>>(
-            dX, T, n, ld, d_q + q0, nqb, (int)W, Mw, sig, tf, ctx->d_status);
+        if (by_ranks)
+            bd_sig_rank_kernel<<<sgrid, 128, 0, st>>>(Rp, T, n, d_q + q0, nqb, (int)W, Mw, sig, tf);
+        else
+            bd_sig_kernel<<<sgrid, 128, 0, st>>>(dX, T, n, ld, d_q + q0, nqb, (int)W, Mw, sig, tf, ctx->d_status);
         SD_TRY(prof_end(ctx));
         SD_TRY(prof_begin(ctx, SD_PHASE_BD_PAIRS));
         bd_match_kernel<<<(unsigned)nqb, BM_THREADS, smem, st>>>(Mw, sig, tf, m, T, (int)W, d_out + q0, flag + q0);

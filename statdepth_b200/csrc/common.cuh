@@ -63,6 +63,7 @@ enum BufId {
     BUF_MISC,       // small odds and ends
     BUF_AUX,        // batched / extra
     BUF_WORK,       // MBD: work list of big parts
+    BUF_RANKS,      // strict BD matcher: per-time-point ranks of all curves (packed pairs)
     NUM_BUFS
 };
 

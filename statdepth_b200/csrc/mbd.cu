@@ -389,7 +389,7 @@ __device__ __forceinline__ double warp_max(double v) {
 struct RankOut {
     u64 *raw2;             // [n] sum over rows of b(b-1) + a(a-1); mbd_finish_kernel turns it into the j = 2 numerator
     i64 *acc3;             // j = 3 numerator, may be null
-    int *rank_b, *rank_a;  // may be null; [row_global*n + c]
+    int *rank_b, *rank_a;  // may be null (rank_a also when rank_b is given); [row_global*n + c]
     i64 n;
     i64 full2, full3;      // C(n-1,2), C(n-1,3)
 };
@@ -405,7 +405,7 @@ __device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, u32 
         if (o.acc3) atomicAdd((u64 *)&o.acc3[c], (u64)(o.full3 - comb3_dev((i64)b) - comb3_dev((i64)a)));
         if (o.rank_b) {
             o.rank_b[row_global * o.n + c] = (int)b;
-            o.rank_a[row_global * o.n + c] = (int)a;
+            if (o.rank_a) o.rank_a[row_global * o.n + c] = (int)a;
         }
     }
 }
