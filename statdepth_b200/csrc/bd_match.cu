@@ -234,7 +234,7 @@ __device__ __forceinline__ bool bm_complement(const uint2 *__restrict__ Mq, cons
 }
 
 // one CTA per query; flag[q] = 1 asks the caller to recompute the query with an enumerating kernel
-__global__ void __launch_bounds__(BM_THREADS) bd_match_kernel(const uint2 *__restrict__ Mw,
+__global__ void __launch_bounds__(BM_THREADS, 2) bd_match_kernel(const uint2 *__restrict__ Mw,
                                                               const ulonglong2 *__restrict__ sig,
                                                               const unsigned char *__restrict__ tf, const i64 m,
                                                               const i64 T, const int W, i64 *__restrict__ out,
