@@ -409,12 +409,10 @@ int bd_strict_match_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, 
     const bool by_ranks = T * n <= (1ll << 26) && nq >= 64;
     u32 *Rp = nullptr;
     if (by_ranks) {
-        SD_TRY(ctx->buf[BUF_RANKS].reserve((size_t)T * n * sizeof(int) + (size_t)TP * n * sizeof(u32) +
-                                           (size_t)n * sizeof(i64)));
-        i64 *acc = ctx->buf[BUF_RANKS].as<i64>();  // 8-byte items first: the 4-byte arrays may have odd lengths
-        int *rank_b = reinterpret_cast<int *>(acc + n);
+        SD_TRY(ctx->buf[BUF_RANKS].reserve((size_t)T * n * sizeof(int) + (size_t)TP * n * sizeof(u32)));
+        int *rank_b = ctx->buf[BUF_RANKS].as<int>();
         Rp = reinterpret_cast<u32 *>(rank_b + (size_t)T * n);
-        SD_TRY(mbd_all_device(ctx, dX, T, n, ld, false, acc, nullptr, rank_b, nullptr));
+        SD_TRY(mbd_all_device(ctx, dX, T, n, ld, false, nullptr, nullptr, rank_b, nullptr));  // ranks only
         SD_TRY(prof_begin(ctx, SD_PHASE_BD_MASKS));
         bd_pack_ranks_kernel<<<(unsigned)ceil_div(TP * n, 256), 256, 0, st>>>(rank_b, T, n, TP, Rp);
         SD_TRY(prof_end(ctx));

@@ -400,7 +400,8 @@ struct RankOut {
 // EXTRA = false drops the j = 3 accumulator and the rank output (the common call) at compile time.
 template <bool EXTRA>
 __device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, u32 c, u32 b, u32 a) {
-    atomicAdd((unsigned long long *)&o.raw2[c], (u64)b * (u64)(b - 1u) + (u64)a * (u64)(a - 1u));
+    if (!EXTRA || o.raw2)  // rank-only calls (no accumulator) skip the RED
+        atomicAdd((unsigned long long *)&o.raw2[c], (u64)b * (u64)(b - 1u) + (u64)a * (u64)(a - 1u));
     if (EXTRA) {
         if (o.acc3) atomicAdd((u64 *)&o.acc3[c], (u64)(o.full3 - comb3_dev((i64)b) - comb3_dev((i64)a)));
         if (o.rank_b) {
@@ -957,6 +958,7 @@ static int pow2ceil_int(i64 v) {
     return p;
 }
 
+// d_acc2 == nullptr (with d_rank_b given): ranks only, nothing is accumulated.
 // Sum over ALL curves of one matrix: d_acc2[c] (and d_acc3[c]) += sum_t term_j(b,a).  The
 // accumulators are zeroed here unless `accumulate` (row blocks of one matrix).  Optional per-(t,c) rank output.
 int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool want_j3, i64 *d_acc2, i64 *d_acc3,
@@ -970,7 +972,11 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         return SD_ERR_UNSUPPORTED;
     }
     cudaStream_t st = ctx->stream;
-    if (!accumulate) {
+    if (!d_acc2 && !d_rank_b) {
+        set_error("mbd: neither an accumulator nor a rank output was given");
+        return SD_ERR_INVALID;
+    }
+    if (!accumulate && d_acc2) {
         SD_CUDA(cudaMemsetAsync(d_acc2, 0, (size_t)n * sizeof(i64), st));
         if (want_j3) SD_CUDA(cudaMemsetAsync(d_acc3, 0, (size_t)n * sizeof(i64), st));
     }
@@ -1016,12 +1022,12 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     SD_TRY(ctx->buf[BUF_WORK].reserve((size_t)Tc * P * sizeof(int2) + (size_t)n * sizeof(u64)));
     int2 *biglist = ctx->buf[BUF_WORK].as<int2>();
     u64 *raw2 = reinterpret_cast<u64 *>(biglist + (size_t)Tc * P);
-    SD_CUDA(cudaMemsetAsync(raw2, 0, (size_t)n * sizeof(u64), st));
+    if (d_acc2) SD_CUDA(cudaMemsetAsync(raw2, 0, (size_t)n * sizeof(u64), st));
 
     SD_CUDA(cudaFuncSetAttribute(mbd_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
 
     RankOut o;
-    o.raw2 = raw2;
+    o.raw2 = d_acc2 ? raw2 : nullptr;
     o.acc3 = want_j3 ? d_acc3 : nullptr;
     o.rank_b = d_rank_b;
     o.rank_a = d_rank_a;
@@ -1090,8 +1096,10 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         ctx->last.launches++;
         SD_CUDA(cudaGetLastError());
     }
-    mbd_finish_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(raw2, d_acc2, n, T * o.full2);
-    ctx->last.launches++;
+    if (d_acc2) {
+        mbd_finish_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(raw2, d_acc2, n, T * o.full2);
+        ctx->last.launches++;
+    }
     SD_CUDA(cudaGetLastError());
     return SD_OK;
 }

@@ -183,7 +183,6 @@ int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride
     if (IB > ninst_total) IB = ninst_total;
     SD_TRY(ctx->buf[BUF_IN2].reserve((size_t)IB * n * 3 * sizeof(double)));
     SD_TRY(ctx->buf[BUF_MASK].reserve((size_t)IB * n * 7 * sizeof(int)));
-    SD_TRY(ctx->buf[BUF_ACC].reserve((size_t)n * 2 * 2 * sizeof(i64)));
     double *KA = ctx->buf[BUF_IN2].as<double>();
     double *KB = KA + (size_t)IB * n;
     int *bA = ctx->buf[BUF_MASK].as<int>();
@@ -191,7 +190,6 @@ int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride
     int *bB = aA + (size_t)IB * n;
     int *aB = bB + (size_t)IB * 2 * n;
     int *claim = aB + (size_t)IB * 2 * n;
-    i64 *acc = ctx->buf[BUF_ACC].as<i64>();
     ScGeom g;
     g.pts = d_pts;
     g.stride_j = stride_j;
@@ -209,8 +207,8 @@ int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride
         sc_keys_kernel<<<dim3(gx, (unsigned)ni), 256, 0, st>>>(g, n, ni, KA, KB, ctx->d_status);
         ctx->last.launches++;
         SD_CUDA(cudaMemsetAsync(claim, 0, (size_t)ni * n * sizeof(int), st));
-        SD_TRY(mbd_all_device(ctx, KA, ni, n, n, false, acc, acc + n, bA, aA));
-        SD_TRY(mbd_all_device(ctx, KB, ni, 2 * n, 2 * n, false, acc, acc + 2 * n, bB, aB));
+        SD_TRY(mbd_all_device(ctx, KA, ni, n, n, false, nullptr, nullptr, bA, aA));  // ranks only
+        SD_TRY(mbd_all_device(ctx, KB, ni, 2 * n, 2 * n, false, nullptr, nullptr, bB, aB));
         sc_reduce_kernel<<<(unsigned)ni, 256, 0, st>>>(g, n, KA, bA, aA, bB, claim, d_out);
         ctx->last.launches++;
         SD_CUDA(cudaGetLastError());
