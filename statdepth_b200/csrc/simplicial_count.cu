@@ -176,20 +176,19 @@ int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride
         set_error("simplicial counting: n=%lld too large", (long long)n);
         return SD_ERR_UNSUPPORTED;
     }
-    // batch size: ~48 n bytes of keys and ranks per instance (+ the rank pipeline's part lists)
+    // batch size: ~44 n bytes of keys and ranks per instance (+ the rank pipeline's part lists)
     i64 IB = (i64)((3ull << 30) / (size_t)(48 * n));
     if (IB < 1) IB = 1;
     if (IB > 32768) IB = 32768;
     if (IB > ninst_total) IB = ninst_total;
     SD_TRY(ctx->buf[BUF_IN2].reserve((size_t)IB * n * 3 * sizeof(double)));
-    SD_TRY(ctx->buf[BUF_MASK].reserve((size_t)IB * n * 7 * sizeof(int)));
+    SD_TRY(ctx->buf[BUF_MASK].reserve((size_t)IB * n * 5 * sizeof(int)));
     double *KA = ctx->buf[BUF_IN2].as<double>();
     double *KB = KA + (size_t)IB * n;
     int *bA = ctx->buf[BUF_MASK].as<int>();
     int *aA = bA + (size_t)IB * n;
     int *bB = aA + (size_t)IB * n;
-    int *aB = bB + (size_t)IB * 2 * n;
-    int *claim = aB + (size_t)IB * 2 * n;
+    int *claim = bB + (size_t)IB * 2 * n;  // the 'above' ranks of the doubled matrix are not needed
     ScGeom g;
     g.pts = d_pts;
     g.stride_j = stride_j;
@@ -208,7 +207,7 @@ int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride
         ctx->last.launches++;
         SD_CUDA(cudaMemsetAsync(claim, 0, (size_t)ni * n * sizeof(int), st));
         SD_TRY(mbd_all_device(ctx, KA, ni, n, n, false, nullptr, nullptr, bA, aA));  // ranks only
-        SD_TRY(mbd_all_device(ctx, KB, ni, 2 * n, 2 * n, false, nullptr, nullptr, bB, aB));
+        SD_TRY(mbd_all_device(ctx, KB, ni, 2 * n, 2 * n, false, nullptr, nullptr, bB, nullptr));
         sc_reduce_kernel<<<(unsigned)ni, 256, 0, st>>>(g, n, KA, bA, aA, bB, claim, d_out);
         ctx->last.launches++;
         SD_CUDA(cudaGetLastError());
