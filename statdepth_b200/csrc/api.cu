@@ -253,14 +253,12 @@ int sd_band_ranks_f64(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_
         SD_TRY(ctx->buf[BUF_IN].reserve((size_t)T * n * sizeof(double)));
         dX = ctx->buf[BUF_IN].as<double>();
     }
-    SD_TRY(ctx->buf[BUF_ACC].reserve((size_t)n * 2 * sizeof(i64)));
     SD_TRY(ctx->buf[BUF_OUT].reserve((size_t)T * n * 2 * sizeof(int)));
     int *d_b = ctx->buf[BUF_OUT].as<int>();
     int *d_a = d_b + (size_t)T * n;
     SD_TRY(mark(ctx, 1));
     if (layout == SD_LAYOUT_NT) SD_TRY(transpose_device(ctx, ctx->buf[BUF_IN2].as<double>(), n, T, T, dX));
-    i64 *acc2 = ctx->buf[BUF_ACC].as<i64>();
-    SD_TRY(mbd_all_device(ctx, dX, T, n, n, false, acc2, acc2 + n, d_b, d_a));
+    SD_TRY(mbd_all_device(ctx, dX, T, n, n, false, nullptr, nullptr, d_b, d_a));  // ranks only
     SD_TRY(mark(ctx, 2));
     SD_CUDA(cudaMemcpyAsync(below_out, d_b, (size_t)T * n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SD_CUDA(cudaMemcpyAsync(above_out, d_a, (size_t)T * n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
