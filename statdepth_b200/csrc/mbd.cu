@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
     if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
     __syncthreads();
     if (tid < 32) {
-        const u32 t = s_wsum[tid];
+        const u32 t = tid < (int)(blockDim.x >> 5) ? s_wsum[tid] : 0u;
         u32 ws = t;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -869,14 +869,10 @@ __device__ void smem_merge_tail(u64 *tile, int len) {
     }
 }
 
-__global__ void __launch_bounds__(1024) mbd_fallback_kernel(const double *__restrict__ X, const i64 n, const i64 ld,
-                                                             const i64 NP, const int *__restrict__ rowflag,
-                                                             u64 *__restrict__ scratch, const i64 row_stride,
-                                                             const i64 row0, const RankOut o,
-                                                             int *__restrict__ status, int *__restrict__ fb_count) {
-    __shared__ u64 tile[FB_TILE];
-    const i64 row = blockIdx.x;
-    if (!(rowflag[row] & 2)) return;
+// ranks one row; all threads of the CTA take part
+__device__ void fallback_row(const double *__restrict__ X, const i64 n, const i64 ld, const i64 NP, u64 *tile,
+                             u64 *__restrict__ scratch, const i64 row_stride, const i64 row0, const RankOut &o,
+                             int *__restrict__ status, int *__restrict__ fb_count, const i64 row) {
     const int tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) atomicAdd(fb_count, 1);
     const double *xr = X + row * ld;
@@ -941,6 +937,21 @@ __global__ void __launch_bounds__(1024) mbd_fallback_kernel(const double *__rest
             if (keys[mid] <= key) lo = mid + 1; else hi = mid;
         }
         emit_rank<true>(o, row0 + row, (u32)c, (u32)b, (u32)(n - lo));
+    }
+}
+
+// persistent over the rows of the block: almost always no row is flagged, and one CTA per row would cost a
+// launch of thousands of idle 1024-thread CTAs per call (4-5 % of a call on short rows)
+__global__ void __launch_bounds__(1024) mbd_fallback_kernel(const double *__restrict__ X, const i64 n, const i64 ld,
+                                                             const i64 NP, const int *__restrict__ rowflag,
+                                                             const i64 rows, u64 *__restrict__ scratch,
+                                                             const i64 row_stride, const i64 row0, const RankOut o,
+                                                             int *__restrict__ status, int *__restrict__ fb_count) {
+    __shared__ u64 tile[FB_TILE];
+    for (i64 row = blockIdx.x; row < rows; row += gridDim.x) {
+        if (!(rowflag[row] & 2)) continue;  // uniform
+        fallback_row(X, n, ld, NP, tile, scratch, row_stride, row0, o, status, fb_count, row);
+        __syncthreads();
     }
 }
 
@@ -1059,7 +1070,11 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             ctx->last.launches++;
             SD_TRY(prof_begin(ctx, SD_PHASE_MBD_RANK));
             // rows with parts of more than CAP values (heavy ties): those parts are ranked from value tables
-            mbd_heavy_kernel<<<(unsigned)rows, HV_THREADS, 0, st>>>(Xb, n, ld, P, splitters_f, tables, cursor, rowflag, pbase,
+            // one thread per part for the prefix; rows with heavy parts scan their values with the same block
+            int hv_threads = 128;
+            while (hv_threads < P) hv_threads <<= 1;
+            if (n > 16384) hv_threads = HV_THREADS;  // long rows: a heavy row scans n values
+            mbd_heavy_kernel<<<(unsigned)rows, hv_threads, 0, st>>>(Xb, n, ld, P, splitters_f, tables, cursor, rowflag, pbase,
                                                                     r0, o);
             RankArgs ra;
             ra.P = P;
@@ -1090,8 +1105,9 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         }
         // rows flagged as overflowing (or all rows when forced): generic path; idle CTAs exit at once
         SD_TRY(prof_begin(ctx, SD_PHASE_MBD_GENERIC));
-        mbd_fallback_kernel<<<(unsigned)rows, 1024, 0, st>>>(Xb, n, ld, NP, rowflag, (u64 *)part_x, NP, r0, o,
-                                                             ctx->d_status, fb_count);
+        const i64 fgrid = rows < 2 * (i64)ctx->sm_count ? rows : 2 * (i64)ctx->sm_count;
+        mbd_fallback_kernel<<<(unsigned)fgrid, 1024, 0, st>>>(Xb, n, ld, NP, rowflag, rows, (u64 *)part_x, NP, r0, o,
+                                                              ctx->d_status, fb_count);
         SD_TRY(prof_end(ctx));
         ctx->last.launches++;
         SD_CUDA(cudaGetLastError());
