@@ -13,19 +13,31 @@
 namespace sd {
 
 // ---------------------------------------------------------------------------------------------
-// L1 depth: one thread per query point, all points streamed through shared memory, float64
-// accumulation in index order (the order of the reference's Python loop, _pointcloud.py:145-146)
+// L1 depth: L1_LANES adjacent lanes per query point, all points streamed through shared memory.  Lane k sums
+// the unit vectors of the points o = k (mod L1_LANES) in index order in float64; the partial sums are added
+// at the end.  (One thread per query kept the reference's exact summation order, _pointcloud.py:145-146, but
+// left 10 warps per SM on 50 000 queries; the order only moves the result by ~1e-16, the bar is 1e-12.)
 // ---------------------------------------------------------------------------------------------
 constexpr int L1_TILE = 512;
 constexpr int L1_MAXD = 16;
+#ifndef SD_L1_LANES
+#define SD_L1_LANES 4
+#endif
+#ifndef SD_L1_ILP
+#define SD_L1_ILP 1
+#endif
+constexpr int L1_LANES = SD_L1_LANES;  // lanes per query (1 would keep the reference's summation order bit for bit)
+constexpr int L1_ILP = SD_L1_ILP;      // points in flight per lane
+constexpr int L1_THREADS = 128;
 
 template <int D>
-__global__ void __launch_bounds__(128) l1_kernel(const double *__restrict__ P, const i64 n, const int d_rt,
-                                                 const i64 *__restrict__ q, const i64 nq,
-                                                 double *__restrict__ out) {
+__global__ void __launch_bounds__(L1_THREADS) l1_kernel(const double *__restrict__ P, const i64 n, const int d_rt,
+                                                        const i64 *__restrict__ q, const i64 nq,
+                                                        double *__restrict__ out) {
     extern __shared__ double s_pts[];  // L1_TILE * d
     const int d = D > 0 ? D : d_rt;
-    const i64 qi = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const int part = threadIdx.x % L1_LANES;
+    const i64 qi = (i64)blockIdx.x * (L1_THREADS / L1_LANES) + threadIdx.x / L1_LANES;
     const bool active = qi < nq;
     const i64 p = active ? (q ? q[qi] : qi) : 0;
     double xp[D > 0 ? D : L1_MAXD], s[D > 0 ? D : L1_MAXD];
@@ -40,47 +52,64 @@ __global__ void __launch_bounds__(128) l1_kernel(const double *__restrict__ P, c
         for (int i = threadIdx.x; i < len * d; i += blockDim.x) s_pts[i] = P[t0 * d + i];
         __syncthreads();
         if (active) {
-            for (int o = 0; o < len; ++o) {
-                if (t0 + o == p) continue;
-                double nrm2 = 0.0, diff[D > 0 ? D : L1_MAXD];
+            // L1_ILP points at a time: their square roots and divisions are independent and overlap; the terms
+            // are then added strictly in index order (adding +0.0 for the point itself changes no bit)
+            for (int o0 = part * L1_ILP; o0 < len; o0 += L1_LANES * L1_ILP) {
+                double term[L1_ILP][D > 0 ? D : L1_MAXD];
 #pragma unroll
-                for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c) {
-                    if (c < d) {
-                        const double xo = s_pts[o * d + c];
-                        diff[c] = xo - xp[c];
-                        const double back = xp[c] - xo;
-                        nrm2 += back * back;
+                for (int u = 0; u < L1_ILP; ++u) {
+                    const int o = o0 + u;
+                    const bool skip = o >= len || t0 + o == p;
+                    double nrm2 = 0.0, diff[D > 0 ? D : L1_MAXD];
+#pragma unroll
+                    for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c) {
+                        diff[c] = 0.0;
+                        if (c < d && o < len) {
+                            const double xo = s_pts[o * d + c];
+                            diff[c] = xo - xp[c];
+                            const double back = xp[c] - xo;
+                            nrm2 += back * back;
+                        }
                     }
-                }
-                const double nrm = sqrt(nrm2);
+                    const double nrm = sqrt(nrm2);
 #pragma unroll
-                for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c)
-                    if (c < d) s[c] += diff[c] / nrm;
+                    for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c)
+                        term[u][c] = skip ? 0.0 : diff[c] / nrm;  // duplicates: 0/0 = NaN propagates, as in the reference
+                }
+#pragma unroll
+                for (int u = 0; u < L1_ILP; ++u)
+#pragma unroll
+                    for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c)
+                        if (c < d) s[c] += term[u][c];
             }
         }
     }
-    if (active) {
-        double tot = 0.0;
+    double tot = 0.0;
 #pragma unroll
-        for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c)
-            if (c < d) tot += s[c] * s[c];
-        out[qi] = 1.0 - sqrt(tot) / (double)n;
+    for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c) {
+        if (c < d) {
+            double v = s[c];
+#pragma unroll
+            for (int m = 1; m < L1_LANES; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+            tot += v * v;
+        }
     }
+    if (active && part == 0) out[qi] = 1.0 - sqrt(tot) / (double)n;
 }
 
 int l1_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 nq, double *d_out) {
     if (nq == 0) return SD_OK;
-    const unsigned grid = (unsigned)ceil_div(nq, 128);
+    const unsigned grid = (unsigned)ceil_div(nq, L1_THREADS / L1_LANES);
     const size_t smem = (size_t)L1_TILE * d * sizeof(double);
     cudaStream_t st = ctx->stream;
     switch (d) {
-        case 1: l1_kernel<1><<<grid, 128, smem, st>>>(dP, n, d, d_q, nq, d_out); break;
-        case 2: l1_kernel<2><<<grid, 128, smem, st>>>(dP, n, d, d_q, nq, d_out); break;
-        case 3: l1_kernel<3><<<grid, 128, smem, st>>>(dP, n, d, d_q, nq, d_out); break;
+        case 1: l1_kernel<1><<<grid, L1_THREADS, smem, st>>>(dP, n, d, d_q, nq, d_out); break;
+        case 2: l1_kernel<2><<<grid, L1_THREADS, smem, st>>>(dP, n, d, d_q, nq, d_out); break;
+        case 3: l1_kernel<3><<<grid, L1_THREADS, smem, st>>>(dP, n, d, d_q, nq, d_out); break;
         default:
             SD_CUDA(cudaFuncSetAttribute(l1_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L1_TILE * L1_MAXD * (int)sizeof(double)));
-            l1_kernel<0><<<grid, 128, smem, st>>>(dP, n, d, d_q, nq, d_out);
+            l1_kernel<0><<<grid, L1_THREADS, smem, st>>>(dP, n, d, d_q, nq, d_out);
             break;
     }
     ctx->last.launches++;
