@@ -15,8 +15,9 @@ namespace sd {
 // ---------------------------------------------------------------------------------------------
 // L1 depth: L1_LANES adjacent lanes per query point, all points streamed through shared memory.  Lane k sums
 // the unit vectors of the points o = k (mod L1_LANES) in index order in float64; the partial sums are added
-// at the end.  (One thread per query kept the reference's exact summation order, _pointcloud.py:145-146, but
-// left 10 warps per SM on 50 000 queries; the order only moves the result by ~1e-16, the bar is 1e-12.)
+// at the end.  (One thread per query with sqrt and divisions repeated the reference's operations bit for bit,
+// _pointcloud.py:145-146, at 12.7 ms for 50 000 points; lanes + rsqrt: 3.9 ms, <= 3e-14 relative on the depth,
+// the bar is 1e-12.)
 // ---------------------------------------------------------------------------------------------
 constexpr int L1_TILE = 512;
 constexpr int L1_MAXD = 16;
@@ -71,10 +72,12 @@ __global__ void __launch_bounds__(L1_THREADS) l1_kernel(const double *__restrict
                             nrm2 += back * back;
                         }
                     }
-                    const double nrm = sqrt(nrm2);
+                    // one reciprocal square root per pair instead of a square root and d divisions (<= 2 ulp per
+                    // term; duplicates: 0 * inf = NaN propagates like the reference's 0 / 0)
+                    const double inv = rsqrt(nrm2);
 #pragma unroll
                     for (int c = 0; c < (D > 0 ? D : L1_MAXD); ++c)
-                        term[u][c] = skip ? 0.0 : diff[c] / nrm;  // duplicates: 0/0 = NaN propagates, as in the reference
+                        term[u][c] = skip ? 0.0 : diff[c] * inv;
                 }
 #pragma unroll
                 for (int u = 0; u < L1_ILP; ++u)
