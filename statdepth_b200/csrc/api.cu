@@ -387,26 +387,57 @@ static int sd_band_depth_batched_f64_impl(sd_ctx *ctx, const double *X, int64_t 
             qloc[(size_t)(b * nqb + i)] = pos[(size_t)g];
         }
     }
+    // relaxed depth with equally sized batches (permutation tests): ALL batches go through the rank pipeline as
+    // one matrix of B*T rows whose row groups accumulate separately -- a handful of launches instead of ~10 per batch
+    bool uniform = relax != 0 && B > 1 && (j == 2 || j == 3);
+    const i64 m0 = B > 0 ? offs[1] - offs[0] : 0;
+    for (i64 b = 0; b < B && uniform; ++b) uniform = offs[(size_t)b + 1] - offs[(size_t)b] == m0;
+    if (uniform && m0 >= 1) {
+        const long double full = (j == 2) ? (long double)(m0 - 1) * (m0 - 2) / 2.0L
+                                          : (long double)(m0 - 1) * (m0 - 2) * (m0 - 3) / 6.0L;
+        if (full * (long double)T >= 9.0e18L) uniform = false;  // let the per-batch path report the overflow
+    }
+    if (uniform && m0 >= 1)
+        for (i64 b = 0; b < B; ++b)  // flat index of every query in the [B][m0] accumulator
+            for (i64 i = 0; i < nqb; ++i) qloc[(size_t)(b * nqb + i)] += b * m0;
     SD_TRY(begin_call(ctx));
     double *dX = nullptr;
     SD_TRY(upload_matrix(ctx, BUF_IN, X, T, n, ld, &dX));
     SD_TRY(ctx->buf[BUF_AUX].reserve((cols.size() + 1) * sizeof(i64)));
     SD_TRY(ctx->buf[BUF_MISC].reserve((qloc.size() + 1) * sizeof(i64)));
     SD_TRY(ctx->buf[BUF_OUT].reserve((qloc.size() + 1) * sizeof(i64)));
-    SD_TRY(ctx->buf[BUF_IN2].reserve((size_t)T * n * sizeof(double)));
     i64 *d_cols = ctx->buf[BUF_AUX].as<i64>();
     i64 *d_ql = ctx->buf[BUF_MISC].as<i64>();
     i64 *d_out = ctx->buf[BUF_OUT].as<i64>();
-    double *dXb = ctx->buf[BUF_IN2].as<double>();
     if (!cols.empty())
         SD_CUDA(cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
     if (!qloc.empty())
         SD_CUDA(cudaMemcpyAsync(d_ql, qloc.data(), qloc.size() * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
     SD_TRY(mark(ctx, 1));
-    for (i64 b = 0; b < B; ++b) {
-        const i64 m = offs[(size_t)b + 1] - offs[(size_t)b];
-        SD_TRY(compact_columns_device(ctx, dX, T, n, d_cols + offs[(size_t)b], m, dXb));
-        SD_TRY(band_depth_device(ctx, dXb, T, m, m, d_ql + b * nqb, nqb, j, relax, d_out + b * nqb));
+    if (uniform && m0 >= 1) {
+        // batches per pass: the gathered matrix stays below ~1 GB
+        i64 BB = (i64)((1ull << 30) / ((size_t)T * m0 * sizeof(double)));
+        if (BB < 1) BB = 1;
+        if (BB > B) BB = B;
+        SD_TRY(ctx->buf[BUF_IN2].reserve((size_t)BB * T * m0 * sizeof(double)));
+        SD_TRY(ctx->buf[BUF_ACC].reserve((size_t)B * m0 * 2 * sizeof(i64)));
+        double *dXg = ctx->buf[BUF_IN2].as<double>();
+        i64 *acc2 = ctx->buf[BUF_ACC].as<i64>(), *acc3 = acc2 + B * m0;
+        for (i64 b0 = 0; b0 < B; b0 += BB) {
+            const i64 nb = B - b0 < BB ? B - b0 : BB;
+            SD_TRY(compact_batches_device(ctx, dX, T, n, d_cols + b0 * m0, m0, nb, dXg));
+            SD_TRY(mbd_all_device(ctx, dXg, nb * T, m0, m0, j == 3, acc2 + b0 * m0, acc3 + b0 * m0, nullptr, nullptr,
+                                  false, T));
+        }
+        SD_TRY(gather_i64_device(ctx, j == 2 ? acc2 : acc3, d_ql, (i64)qloc.size(), d_out));
+    } else {
+        SD_TRY(ctx->buf[BUF_IN2].reserve((size_t)T * n * sizeof(double)));
+        double *dXb = ctx->buf[BUF_IN2].as<double>();
+        for (i64 b = 0; b < B; ++b) {
+            const i64 m = offs[(size_t)b + 1] - offs[(size_t)b];
+            SD_TRY(compact_columns_device(ctx, dX, T, n, d_cols + offs[(size_t)b], m, dXb));
+            SD_TRY(band_depth_device(ctx, dXb, T, m, m, d_ql + b * nqb, nqb, j, relax, d_out + b * nqb));
+        }
     }
     SD_TRY(mark(ctx, 2));
     if (!qloc.empty())

@@ -154,6 +154,26 @@ int gather_i64_device(sd_ctx *ctx, const i64 *d_src, const i64 *d_idx, i64 nq, i
     return SD_OK;
 }
 
+// out[(b*T + t)*m + k] = X[t*n + cols[b*m + k]] for nb batches of m member columns each
+__global__ void compact_batches_kernel(const double *__restrict__ X, i64 T, i64 n, const i64 *__restrict__ cols,
+                                       i64 m, i64 nb, double *__restrict__ out) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb * T * m) return;
+    const i64 k = i % m, bt = i / m;
+    const i64 t = bt % T, b = bt / T;
+    out[i] = X[t * n + cols[b * m + k]];
+}
+
+int compact_batches_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, const i64 *d_cols, i64 m, i64 nb,
+                           double *d_out) {
+    if (nb * T * m == 0) return SD_OK;
+    compact_batches_kernel<<<(unsigned)ceil_div(nb * T * m, 256), 256, 0, ctx->stream>>>(dX, T, n, d_cols, m, nb,
+                                                                                          d_out);
+    ctx->last.launches++;
+    SD_CUDA(cudaGetLastError());
+    return SD_OK;
+}
+
 // out[t*m + k] = X[t*n + cols[k]]
 __global__ void compact_columns_kernel(const double *__restrict__ X, i64 T, i64 n, const i64 *__restrict__ cols,
                                        i64 m, double *__restrict__ out) {

@@ -392,18 +392,24 @@ struct RankOut {
     int *rank_b, *rank_a;  // may be null (rank_a also when rank_b is given); [row_global*n + c]
     i64 n;
     i64 full2, full3;      // C(n-1,2), C(n-1,3)
+    i64 group_rows;        // 0: one accumulator row; g > 0: rows [k*g, (k+1)*g) accumulate into row k of [G][n]
 };
+
+__device__ __forceinline__ i64 acc_offset(const RankOut &o, const i64 row_global) {
+    return o.group_rows ? (row_global / o.group_rows) * o.n : 0;
+}
 
 // One (row, curve) result.  The j = 2 term C(n-1,2) - C(b,2) - C(a,2) is accumulated as the raw sum
 // b(b-1) + a(a-1) (two 32x32->64 multiply-adds and one RED; m = 0 gives 0 * (2^32-1) = 0) and finished once
 // per call by mbd_finish_kernel: numerator += rows * C(n-1,2) - raw / 2.  b, a < 2^31.
 // EXTRA = false drops the j = 3 accumulator and the rank output (the common call) at compile time.
 template <bool EXTRA>
-__device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, u32 c, u32 b, u32 a) {
+__device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, i64 acc_off, u32 c, u32 b, u32 a) {
     if (!EXTRA || o.raw2)  // rank-only calls (no accumulator) skip the RED
-        atomicAdd((unsigned long long *)&o.raw2[c], (u64)b * (u64)(b - 1u) + (u64)a * (u64)(a - 1u));
+        atomicAdd((unsigned long long *)&o.raw2[acc_off + c], (u64)b * (u64)(b - 1u) + (u64)a * (u64)(a - 1u));
     if (EXTRA) {
-        if (o.acc3) atomicAdd((u64 *)&o.acc3[c], (u64)(o.full3 - comb3_dev((i64)b) - comb3_dev((i64)a)));
+        if (o.acc3)
+            atomicAdd((u64 *)&o.acc3[acc_off + c], (u64)(o.full3 - comb3_dev((i64)b) - comb3_dev((i64)a)));
         if (o.rank_b) {
             o.rank_b[row_global * o.n + c] = (int)b;
             if (o.rank_a) o.rank_a[row_global * o.n + c] = (int)a;
@@ -411,9 +417,11 @@ __device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, u32 
     }
 }
 
-__global__ void mbd_finish_kernel(const u64 *__restrict__ raw2, i64 *__restrict__ acc2, const i64 n, const i64 rows_full2) {
+// count = number of accumulator entries (n per group)
+__global__ void mbd_finish_kernel(const u64 *__restrict__ raw2, i64 *__restrict__ acc2, const i64 count,
+                                  const i64 rows_full2) {
     const i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n) acc2[c] += rows_full2 - (i64)(raw2[c] >> 1);
+    if (c < count) acc2[c] += rows_full2 - (i64)(raw2[c] >> 1);
 }
 
 // Runs of equal 22-bit keys in a sorted part (collisions of distinct values, or true ties).  The caller has
@@ -501,6 +509,7 @@ __device__ __forceinline__ void rank_part(const float *__restrict__ px, const u3
                                           const i64 row_global, const RankOut &o, u32 *skeys, u32 *sres, u32 *sflag,
                                           const int lane, float lo, float hi, const bool have_range) {
     const u32 n32 = (u32)o.n;
+    const i64 acc_off = acc_offset(o, row_global);
     if (!have_range) {
         lo = INFINITY;
         hi = -INFINITY;
@@ -578,7 +587,7 @@ __device__ __forceinline__ void rank_part(const float *__restrict__ px, const u3
 #pragma unroll
         for (int u = 0; u < EMIT_DEPTH; ++u)
             if (s0 + 32 * u < cnt)
-                emit_rank<EXTRA>(o, row_global, j[u], base + (res[u] & 0xffffu), n32 - base - (res[u] >> 16));
+                emit_rank<EXTRA>(o, row_global, acc_off, j[u], base + (res[u] & 0xffffu), n32 - base - (res[u] >> 16));
     }
     __syncwarp();
 }
@@ -806,6 +815,7 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
         }
         tbelow[h][k] = below;
     }
+    const i64 acc_off = acc_offset(o, row0 + row);
     __syncthreads();
     for (i64 c0 = tid; c0 < n; c0 += (i64)HV_UNROLL * blockDim.x) {
         double xs[HV_UNROLL];
@@ -825,7 +835,7 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
             if (h < 0) continue;
             const int k = hv_find(tab[h], (u64)__double_as_longlong(x + 0.0));
             const u32 b = base[part] + (u32)tbelow[h][k];
-            emit_rank<true>(o, row0 + row, (u32)c, b, (u32)n - b - (u32)tcnt[h][k]);
+            emit_rank<true>(o, row0 + row, acc_off, (u32)c, b, (u32)n - b - (u32)tcnt[h][k]);
         }
     }
 }
@@ -923,6 +933,7 @@ __device__ void fallback_row(const double *__restrict__ X, const i64 n, const i6
         }
     }
     // ranks by binary search in the sorted keys (first n entries are the real ones)
+    const i64 acc_off = acc_offset(o, row0 + row);
     for (i64 c = tid; c < n; c += nt) {
         const u64 key = sortable_key(xr[c]);
         i64 lo = 0, hi = n;  // lower bound: first index with keys[idx] >= key
@@ -936,7 +947,7 @@ __device__ void fallback_row(const double *__restrict__ X, const i64 n, const i6
             const i64 mid = (lo + hi) >> 1;
             if (keys[mid] <= key) lo = mid + 1; else hi = mid;
         }
-        emit_rank<true>(o, row0 + row, (u32)c, (u32)b, (u32)(n - lo));
+        emit_rank<true>(o, row0 + row, acc_off, (u32)c, (u32)b, (u32)(n - lo));
     }
 }
 
@@ -972,8 +983,10 @@ static int pow2ceil_int(i64 v) {
 // d_acc2 == nullptr (with d_rank_b given): ranks only, nothing is accumulated.
 // Sum over ALL curves of one matrix: d_acc2[c] (and d_acc3[c]) += sum_t term_j(b,a).  The
 // accumulators are zeroed here unless `accumulate` (row blocks of one matrix).  Optional per-(t,c) rank output.
+// group_rows = g > 0: the T rows are G = T / g independent matrices of g rows each (same n); d_acc2 / d_acc3
+// are [G][n] and matrix k accumulates into row k (batched permutations: one launch sequence for all of them).
 int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool want_j3, i64 *d_acc2, i64 *d_acc3,
-                   int *d_rank_b, int *d_rank_a, bool accumulate) {
+                   int *d_rank_b, int *d_rank_a, bool accumulate, i64 group_rows) {
     if (n < 1 || T < 0 || ld < n) {
         set_error("mbd: bad shape T=%lld n=%lld ld=%lld", (long long)T, (long long)n, (long long)ld);
         return SD_ERR_INVALID;
@@ -982,14 +995,20 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         set_error("mbd: n=%lld exceeds 2^31-1", (long long)n);
         return SD_ERR_UNSUPPORTED;
     }
+    if (group_rows < 0 || (group_rows > 0 && T % group_rows != 0)) {
+        set_error("mbd: %lld rows are not a multiple of the group size %lld", (long long)T, (long long)group_rows);
+        return SD_ERR_INVALID;
+    }
+    const i64 groups = group_rows > 0 ? T / group_rows : 1;
+    const i64 acc_len = n * (groups > 0 ? groups : 1);
     cudaStream_t st = ctx->stream;
     if (!d_acc2 && !d_rank_b) {
         set_error("mbd: neither an accumulator nor a rank output was given");
         return SD_ERR_INVALID;
     }
     if (!accumulate && d_acc2) {
-        SD_CUDA(cudaMemsetAsync(d_acc2, 0, (size_t)n * sizeof(i64), st));
-        if (want_j3) SD_CUDA(cudaMemsetAsync(d_acc3, 0, (size_t)n * sizeof(i64), st));
+        SD_CUDA(cudaMemsetAsync(d_acc2, 0, (size_t)acc_len * sizeof(i64), st));
+        if (want_j3) SD_CUDA(cudaMemsetAsync(d_acc3, 0, (size_t)acc_len * sizeof(i64), st));
     }
     if (T == 0) return SD_OK;
 
@@ -1030,10 +1049,10 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     float *splitters_f = ctx->buf[BUF_SPLIT].as<float>();
     unsigned short *tables = reinterpret_cast<unsigned short *>(splitters_f + (size_t)Tc * (P > 1 ? P - 1 : 1));
     int *fb_count = ctx->d_status + 1;
-    SD_TRY(ctx->buf[BUF_WORK].reserve((size_t)Tc * P * sizeof(int2) + (size_t)n * sizeof(u64)));
+    SD_TRY(ctx->buf[BUF_WORK].reserve((size_t)Tc * P * sizeof(int2) + (size_t)acc_len * sizeof(u64)));
     int2 *biglist = ctx->buf[BUF_WORK].as<int2>();
     u64 *raw2 = reinterpret_cast<u64 *>(biglist + (size_t)Tc * P);
-    if (d_acc2) SD_CUDA(cudaMemsetAsync(raw2, 0, (size_t)n * sizeof(u64), st));
+    if (d_acc2) SD_CUDA(cudaMemsetAsync(raw2, 0, (size_t)acc_len * sizeof(u64), st));
 
     SD_CUDA(cudaFuncSetAttribute(mbd_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
 
@@ -1045,6 +1064,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     o.n = n;
     o.full2 = (n - 1) * (n - 2) / 2;
     o.full3 = n - 1 < 3 ? 0 : ((n - 1) * (n - 2) / 2) * (n - 3) / 3;
+    o.group_rows = group_rows;
 
     for (i64 r0 = 0; r0 < T; r0 += Tc) {
         const i64 rows = T - r0 < Tc ? T - r0 : Tc;
@@ -1113,7 +1133,8 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         SD_CUDA(cudaGetLastError());
     }
     if (d_acc2) {
-        mbd_finish_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(raw2, d_acc2, n, T * o.full2);
+        mbd_finish_kernel<<<(unsigned)ceil_div(acc_len, 256), 256, 0, st>>>(raw2, d_acc2, acc_len,
+                                                                            (group_rows > 0 ? group_rows : T) * o.full2);
         ctx->last.launches++;
     }
     SD_CUDA(cudaGetLastError());

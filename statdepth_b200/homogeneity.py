@@ -188,27 +188,28 @@ def _perm_stats_batched(pooled: pd.DataFrame, nF: int, perms: np.ndarray, method
             cnt = cnt / float(T)
         return cnt / binom(sizes, 2)[:, None]
 
+    rows = np.arange(B)[:, None]
     # (1) depth of every curve of G_b inside G_b  -> deepest curve of G_b
     memG = np.zeros((B, n), dtype=np.uint8)
-    for b in range(B):
-        memG[b, perms[b, nF:]] = 1
+    memG[rows, perms[:, nF:]] = 1
     qG = np.ascontiguousarray(perms[:, nF:])
     dG = depths(memG, qG, np.full(B, nG))
-    deepest = np.empty(B, dtype=np.int64)
-    for b in range(B):
+    # deepest = first label of sort_values(ascending=False); without a tie at the maximum that is the argmax,
+    # with one the pandas call itself decides (its sort is not stable)
+    deepest = qG[np.arange(B), dG.argmax(axis=1)]
+    tied = np.flatnonzero((dG == dG.max(axis=1, keepdims=True)).sum(axis=1) > 1)
+    for b in tied:
         deepest[b] = pd.Series(index=qG[b], data=dG[b]).sort_values(ascending=False).index[0]
     # (2) depth of that curve inside F_b u {g}
     memF = np.zeros((B, n), dtype=np.uint8)
-    for b in range(B):
-        memF[b, perms[b, :nF]] = 1
-        memF[b, deepest[b]] = 1
+    memF[rows, perms[:, :nF]] = 1
+    memF[np.arange(B), deepest] = 1
     g_in_F = depths(memF, deepest[:, None], np.full(B, nF + 1))[:, 0]
     if method == 'p1':
         return g_in_F
     # (3) p2: | depth(g in F u {g}) - max depth of F_b in F_b |
     memF0 = np.zeros((B, n), dtype=np.uint8)
-    for b in range(B):
-        memF0[b, perms[b, :nF]] = 1
+    memF0[rows, perms[:, :nF]] = 1
     dF = depths(memF0, np.ascontiguousarray(perms[:, :nF]), np.full(B, nF))
     return np.abs(g_in_F - dF.max(axis=1))
 

@@ -410,6 +410,21 @@ def test_k_sampled_and_batched(engine, oracle, golden):
             sub = np.ascontiguousarray(X[:, cols])
             exp = oracle.mbd_counts_all(sub)[loc] if relax else oracle.bd_counts(sub, loc)
             assert (got[b] == exp).all()
+    # equally sized batches (what a permutation test asks for): relaxed depth runs all batches as ONE grouped pass
+    B, m = 9, 40
+    members = np.stack([np.sort(rng.choice(90, m, replace=False)) for _ in range(B)])
+    mem = np.zeros((B, 90), dtype=np.uint8)
+    for b in range(B):
+        mem[b, members[b]] = 1
+    qs = np.stack([rng.permutation(members[b])[:11] for b in range(B)])
+    Xt = np.round(X)  # with ties
+    for Xm in (X, Xt):
+        for j in (2, 3):
+            got = engine.band_depth_counts_batched(Xm, mem, qs, j, True)
+            for b in range(B):
+                loc = [int(np.searchsorted(members[b], g)) for g in qs[b]]
+                exp = oracle.mbd_counts_all(np.ascontiguousarray(Xm[:, members[b]]), j=j)[loc]
+                assert (got[b] == exp).all(), (b, j)
 
 
 def test_reference_test_suite_types():
