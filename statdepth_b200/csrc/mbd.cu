@@ -402,7 +402,7 @@ __device__ __forceinline__ i64 acc_offset(const RankOut &o, const i64 row_global
 // One (row, curve) result.  The j = 2 term C(n-1,2) - C(b,2) - C(a,2) is accumulated as the raw sum
 // b(b-1) + a(a-1) (two 32x32->64 multiply-adds and one RED; m = 0 gives 0 * (2^32-1) = 0) and finished once
 // per call by mbd_finish_kernel: numerator += rows * C(n-1,2) - raw / 2.  b, a < 2^31.
-// EXTRA = false drops the j = 3 accumulator and the rank output (the common call) at compile time.
+// EXTRA = false drops the j = 3 accumulator, the rank output and the row groups (the common call) at compile time.
 template <bool EXTRA>
 __device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, i64 acc_off, u32 c, u32 b, u32 a) {
     if (!EXTRA || o.raw2)  // rank-only calls (no accumulator) skip the RED
@@ -509,7 +509,6 @@ __device__ __forceinline__ void rank_part(const float *__restrict__ px, const u3
                                           const i64 row_global, const RankOut &o, u32 *skeys, u32 *sres, u32 *sflag,
                                           const int lane, float lo, float hi, const bool have_range) {
     const u32 n32 = (u32)o.n;
-    const i64 acc_off = acc_offset(o, row_global);
     if (!have_range) {
         lo = INFINITY;
         hi = -INFINITY;
@@ -573,6 +572,7 @@ __device__ __forceinline__ void rank_part(const float *__restrict__ px, const u3
     // emission in slot order (coalesced curve ids).  The RED's address waits for its id: a one-at-a-time loop
     // spent 40 % of the kernel's stall samples here, so EMIT_DEPTH ids are fetched a step ahead (the first
     // group before the sort).
+    const i64 acc_off = EXTRA ? acc_offset(o, row_global) : 0;  // grouped calls take the EXTRA instantiation
 #pragma unroll 1
     for (int s0 = lane; s0 < cnt; s0 += 32 * EMIT_DEPTH) {
         u32 j[EMIT_DEPTH], res[EMIT_DEPTH];
@@ -1113,7 +1113,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             SD_CUDA(cudaMemsetAsync(ctx->d_status + 2, 0, 2 * sizeof(int), st));
             const dim3 rgrid((unsigned)ceil_div(P, RANK_WARPS), (unsigned)rows);
             const unsigned bgrid = (unsigned)(ctx->sm_count * 4);
-            if (o.acc3 || o.rank_b) {
+            if (o.acc3 || o.rank_b || o.group_rows) {
                 mbd_rank_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
                 mbd_rank_big_kernel<true><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
             } else {
