@@ -389,15 +389,17 @@ static int sd_band_depth_batched_f64_impl(sd_ctx *ctx, const double *X, int64_t 
     }
     // relaxed depth with equally sized batches (permutation tests): ALL batches go through the rank pipeline as
     // one matrix of B*T rows whose row groups accumulate separately -- a handful of launches instead of ~10 per batch
-    bool uniform = relax != 0 && B > 1 && (j == 2 || j == 3);
+    const bool strict_match = !relax && j == 2 && (ctx->bd_impl == SD_BD_AUTO || ctx->bd_impl == SD_BD_MATCH);
+    bool uniform = B > 1 && ((relax != 0 && (j == 2 || j == 3)) || strict_match);
     const i64 m0 = B > 0 ? offs[1] - offs[0] : 0;
     for (i64 b = 0; b < B && uniform; ++b) uniform = offs[(size_t)b + 1] - offs[(size_t)b] == m0;
-    if (uniform && m0 >= 1) {
+    if (uniform && !relax && !bd_match_supported(T, m0)) uniform = false;
+    if (uniform && m0 >= 1 && relax) {
         const long double full = (j == 2) ? (long double)(m0 - 1) * (m0 - 2) / 2.0L
                                           : (long double)(m0 - 1) * (m0 - 2) * (m0 - 3) / 6.0L;
         if (full * (long double)T >= 9.0e18L) uniform = false;  // let the per-batch path report the overflow
     }
-    if (uniform && m0 >= 1)
+    if (uniform && m0 >= 1 && relax)
         for (i64 b = 0; b < B; ++b)  // flat index of every query in the [B][m0] accumulator
             for (i64 i = 0; i < nqb; ++i) qloc[(size_t)(b * nqb + i)] += b * m0;
     SD_TRY(begin_call(ctx));
@@ -426,10 +428,16 @@ static int sd_band_depth_batched_f64_impl(sd_ctx *ctx, const double *X, int64_t 
         for (i64 b0 = 0; b0 < B; b0 += BB) {
             const i64 nb = B - b0 < BB ? B - b0 : BB;
             SD_TRY(compact_batches_device(ctx, dX, T, n, d_cols + b0 * m0, m0, nb, dXg));
-            SD_TRY(mbd_all_device(ctx, dXg, nb * T, m0, m0, j == 3, acc2 + b0 * m0, acc3 + b0 * m0, nullptr, nullptr,
-                                  false, T));
+            if (relax) {
+                SD_TRY(mbd_all_device(ctx, dXg, nb * T, m0, m0, j == 3, acc2 + b0 * m0, acc3 + b0 * m0, nullptr,
+                                      nullptr, false, T));
+            } else {  // strict: sign-vector matcher over all sub-populations of the pass
+                ctx->last.bd_impl_used = SD_BD_MATCH;
+                SD_TRY(bd_strict_match_batched_device(ctx, dXg, nb, T, m0, d_ql + b0 * nqb, nqb, d_out + b0 * nqb,
+                                                      strict_enumerate));
+            }
         }
-        SD_TRY(gather_i64_device(ctx, j == 2 ? acc2 : acc3, d_ql, (i64)qloc.size(), d_out));
+        if (relax) SD_TRY(gather_i64_device(ctx, j == 2 ? acc2 : acc3, d_ql, (i64)qloc.size(), d_out));
     } else {
         SD_TRY(ctx->buf[BUF_IN2].reserve((size_t)T * n * sizeof(double)));
         double *dXb = ctx->buf[BUF_IN2].as<double>();

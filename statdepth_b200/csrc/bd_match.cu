@@ -131,8 +131,11 @@ __global__ void __launch_bounds__(128) bd_sig_kernel(const double *__restrict__ 
 constexpr u32 BM_GUARD = 0x80008000u;
 
 // Rp[tp*n + c] = rank[2tp][c] | rank[2tp+1][c] << 16; time points past T get rank 0 for everybody (a tie)
+// (blockIdx.y = batch: every batch has its own T rank rows and TP packed rows)
 __global__ void bd_pack_ranks_kernel(const int *__restrict__ rank_b, const i64 T, const i64 n, const i64 TP,
                                      u32 *__restrict__ Rp) {
+    rank_b += (i64)blockIdx.y * T * n;
+    Rp += (i64)blockIdx.y * TP * n;
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= TP * n) return;
     const i64 tp = i / n, c = i - tp * n;
@@ -142,12 +145,21 @@ __global__ void bd_pack_ranks_kernel(const int *__restrict__ rank_b, const i64 T
     Rp[i] = lo | (hi << 16);
 }
 
+// blockIdx.z = batch (batched permutation calls): every batch has its own packed ranks, nqb queries and outputs
 __global__ void __launch_bounds__(128) bd_sig_rank_kernel(const u32 *__restrict__ Rp, const i64 T, const i64 n,
                                                           const i64 *__restrict__ qidx, const int nqb, const int W,
                                                           uint2 *__restrict__ Mw, ulonglong2 *__restrict__ sig,
                                                           unsigned char *__restrict__ tf) {
     __shared__ u32 sq[16][BM_SQ];
     __shared__ i64 sqi[BM_SQ];
+    {
+        const i64 z = blockIdx.z;
+        Rp += z * (i64)W * 16 * n;
+        qidx += z * nqb;
+        Mw += z * (i64)nqb * W * (n - 1);
+        sig += z * (i64)nqb * (n - 1);
+        tf += z * (i64)nqb * (n - 1);
+    }
     const int q0 = blockIdx.y * BM_SQ;
     if (threadIdx.x < BM_SQ) sqi[threadIdx.x] = q0 + threadIdx.x < nqb ? qidx[q0 + threadIdx.x] : -1;
     const i64 m = n - 1;
@@ -241,16 +253,27 @@ __device__ __forceinline__ bool bm_complement(const uint2 *__restrict__ Mq, cons
 }
 
 // one CTA per query; flag[q] = 1 asks the caller to recompute the query with an enumerating kernel
-__global__ void __launch_bounds__(BM_THREADS, 2) bd_match_kernel(const uint2 *__restrict__ Mw,
+// NT threads sort up to 16 * NT keys: NT = 512 for the general case (m <= 8192), NT = 64 / 32 when the other
+// curves of a query fit 1024 / 512 keys (permutation batches), where a 8192-slot sort would be 16-32x overwork.
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 8) bd_match_kernel(const uint2 *__restrict__ Mw,
                                                               const ulonglong2 *__restrict__ sig,
                                                               const unsigned char *__restrict__ tf, const i64 m,
                                                               const i64 T, const int W, i64 *__restrict__ out,
                                                               unsigned char *__restrict__ flag) {
     extern __shared__ __align__(16) unsigned char bm_smem[];
-    u64 *skey = reinterpret_cast<u64 *>(bm_smem);  // BM_MAXM keys
+    u64 *skey = reinterpret_cast<u64 *>(bm_smem);  // (NT * 16) keys
+    {   // blockIdx.y = batch: gridDim.x queries per batch
+        const i64 z = (i64)blockIdx.y * gridDim.x;
+        Mw += z * W * m;
+        sig += z * m;
+        tf += z * m;
+        out += z;
+        flag += z;
+    }
     __shared__ int s_z[BM_ZCAP];
     __shared__ int s_nz, s_bad;
-    __shared__ u64 s_red[BM_THREADS / 32];
+    __shared__ u64 s_red[NT / 32];
     const int q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint2 *Mq = Mw + (i64)q * W * m;
@@ -277,7 +300,7 @@ __global__ void __launch_bounds__(BM_THREADS, 2) bd_match_kernel(const uint2 *__
     }
     // 2. sort: 512 keys per warp on registers, then 4 merge levels through swizzled shared memory
     warp_bitonic_sort<BM_EPL, u64>(v, lane);
-    for (int k = 1024; k <= BM_MAXM; k <<= 1) {
+    for (int k = 1024; k <= (NT * 16); k <<= 1) {
         for (int j = k; j >= 1024; j >>= 1) {  // j == k: mirror stage (g ^ (k-1)); else xor stage (g ^ j/2)
             __syncthreads();
 #pragma unroll
@@ -304,7 +327,7 @@ __global__ void __launch_bounds__(BM_THREADS, 2) bd_match_kernel(const uint2 *__
 
     // 3. every run of equal hashes must hold one sign vector; look up every curve's complement
     u64 twice = 0;  // sum over o in F of #{o' in F : B_o' == A_o}
-    for (int p = tid; p < nF && !bad; p += BM_THREADS) {
+    for (int p = tid; p < nF && !bad; p += NT) {
         const u64 key = skey[bm_swz(p)];
         const int o = (int)(key & BM_IDMASK);
         const u64 h = key >> 13;
@@ -337,7 +360,7 @@ __global__ void __launch_bounds__(BM_THREADS, 2) bd_match_kernel(const uint2 *__
     if (!bad) {
         for (int zi = 0; zi < nz; ++zi) {
             const int z = s_z[zi];
-            for (int o = tid; o < m; o += BM_THREADS) {
+            for (int o = tid; o < m; o += NT) {
                 if (o == z || (!tq[o] && o < z)) continue;
                 bool ok = true;
                 for (int w = 0; w < W && ok; ++w) {
@@ -356,7 +379,7 @@ __global__ void __launch_bounds__(BM_THREADS, 2) bd_match_kernel(const uint2 *__
     __syncthreads();
     if (tid == 0) {
         u64 t2 = 0;
-        for (int w = 0; w < BM_THREADS / 32; ++w) t2 += s_red[w];
+        for (int w = 0; w < NT / 32; ++w) t2 += s_red[w];
         out[q] = (i64)(t2 >> 1);
         flag[q] = s_bad ? 1 : 0;
     }
@@ -375,6 +398,22 @@ __global__ void bm_scatter_kernel(const i64 *__restrict__ src, const i64 *__rest
 __global__ void bm_iota_kernel(i64 *p, i64 count) {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) p[i] = i;
+}
+
+// picks the smallest sort capacity that holds the m other curves of a query
+static int launch_match(cudaStream_t st, dim3 grid, i64 m, const uint2 *Mw, const ulonglong2 *sig,
+                        const unsigned char *tf, i64 T, int W, i64 *out, unsigned char *flag) {
+    if (m <= 512) {
+        bd_match_kernel<32><<<grid, 32, 32 * 16 * sizeof(u64), st>>>(Mw, sig, tf, m, T, W, out, flag);
+    } else if (m <= 1024) {
+        bd_match_kernel<64><<<grid, 64, 64 * 16 * sizeof(u64), st>>>(Mw, sig, tf, m, T, W, out, flag);
+    } else {
+        const size_t smem = (size_t)BM_MAXM * sizeof(u64);
+        SD_CUDA(cudaFuncSetAttribute(bd_match_kernel<BM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bd_match_kernel<BM_THREADS><<<grid, BM_THREADS, smem, st>>>(Mw, sig, tf, m, T, W, out, flag);
+    }
+    SD_CUDA(cudaGetLastError());
+    return SD_OK;
 }
 
 bool bd_match_supported(i64 T, i64 n) { return n - 1 <= BM_MAXM && n >= 3 && ceil_div(T, 32) <= 4096; }
@@ -401,8 +440,6 @@ int bd_strict_match_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, 
     if (QB < BM_SQ) QB = BM_SQ;
     if (QB > 32768) QB = 32768;
     if (QB > nq) QB = nq;
-    const size_t smem = (size_t)BM_MAXM * sizeof(u64);
-    SD_CUDA(cudaFuncSetAttribute(bd_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // ranks of all curves at every time point (one pass of the rank pipeline), packed in pairs for the signature
     // kernel; very long series keep the float64 signature kernel (the rank matrix would not pay)
     const i64 TP = W * 16;
@@ -414,7 +451,7 @@ int bd_strict_match_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, 
         Rp = reinterpret_cast<u32 *>(rank_b + (size_t)T * n);
         SD_TRY(mbd_all_device(ctx, dX, T, n, ld, false, nullptr, nullptr, rank_b, nullptr));  // ranks only
         SD_TRY(prof_begin(ctx, SD_PHASE_BD_MASKS));
-        bd_pack_ranks_kernel<<<(unsigned)ceil_div(TP * n, 256), 256, 0, st>>>(rank_b, T, n, TP, Rp);
+        bd_pack_ranks_kernel<<<dim3((unsigned)ceil_div(TP * n, 256), 1), 256, 0, st>>>(rank_b, T, n, TP, Rp);
         SD_TRY(prof_end(ctx));
         ctx->last.launches++;
     }
@@ -435,7 +472,7 @@ int bd_strict_match_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, 
             bd_sig_kernel<<<sgrid, 128, 0, st>>>(dX, T, n, ld, d_q + q0, nqb, (int)W, Mw, sig, tf, ctx->d_status);
         SD_TRY(prof_end(ctx));
         SD_TRY(prof_begin(ctx, SD_PHASE_BD_PAIRS));
-        bd_match_kernel<<<(unsigned)nqb, BM_THREADS, smem, st>>>(Mw, sig, tf, m, T, (int)W, d_out + q0, flag + q0);
+        SD_TRY(launch_match(st, dim3((unsigned)nqb, 1), m, Mw, sig, tf, T, (int)W, d_out + q0, flag + q0));
         SD_TRY(prof_end(ctx));
         ctx->last.launches += 2;
         SD_CUDA(cudaGetLastError());
@@ -461,6 +498,74 @@ int bd_strict_match_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, 
     bm_scatter_kernel<<<(unsigned)ceil_div(nf, 256), 256, 0, st>>>(d_osub, d_pos, nf, d_out);
     ctx->last.launches++;
     SD_CUDA(cudaGetLastError());
+    return SD_OK;
+}
+
+// Strict J = 2 numerators of nb equally shaped matrices (dXg = [nb][T][n], nqb queries each: d_ql[nb][nqb] are
+// positions inside their matrix).  One rank pass, one pack, and one signature + one match launch per chunk of
+// matrices instead of ~9 launches and two host synchronisations per matrix (permutation tests).
+int bd_strict_match_batched_device(sd_ctx *ctx, const double *dXg, i64 nb, i64 T, i64 n, const i64 *d_ql, i64 nqb,
+                                   i64 *d_out,
+                                   int (*fallback)(sd_ctx *, const double *, i64, i64, i64, const i64 *, i64, i64 *)) {
+    cudaStream_t st = ctx->stream;
+    if (nb == 0 || nqb == 0) return SD_OK;
+    const i64 m = n - 1;
+    const i64 W = ceil_div(T, 32), TP = W * 16;
+    SD_TRY(ctx->buf[BUF_RANKS].reserve((size_t)nb * T * n * sizeof(int) + (size_t)nb * TP * n * sizeof(u32)));
+    int *rank_b = ctx->buf[BUF_RANKS].as<int>();
+    u32 *Rp = reinterpret_cast<u32 *>(rank_b + (size_t)nb * T * n);
+    SD_TRY(mbd_all_device(ctx, dXg, nb * T, n, n, false, nullptr, nullptr, rank_b, nullptr));  // ranks only
+    SD_TRY(prof_begin(ctx, SD_PHASE_BD_MASKS));
+    bd_pack_ranks_kernel<<<dim3((unsigned)ceil_div(TP * n, 256), (unsigned)nb), 256, 0, st>>>(rank_b, T, n, TP, Rp);
+    SD_TRY(prof_end(ctx));
+    ctx->last.launches++;
+    const size_t per_b = (size_t)nqb * ((size_t)W * m * sizeof(uint2) + (size_t)m * (sizeof(ulonglong2) + 1));
+    i64 CB = (i64)((3ull << 29) / (per_b > 0 ? per_b : 1));  // matrices per launch pair: ~1.5 GB of sign words
+    if (CB < 1) CB = 1;
+    if (CB > nb) CB = nb;
+    if (CB > 65535) CB = 65535;
+    SD_TRY(ctx->buf[BUF_MASK].reserve((size_t)CB * nqb * W * m * sizeof(uint2)));
+    SD_TRY(ctx->buf[BUF_PART_X].reserve((size_t)CB * nqb * m * (sizeof(ulonglong2) + 1) + (size_t)nb * nqb + 64));
+    uint2 *Mw = ctx->buf[BUF_MASK].as<uint2>();
+    ulonglong2 *sig = ctx->buf[BUF_PART_X].as<ulonglong2>();
+    unsigned char *tf = reinterpret_cast<unsigned char *>(sig + (size_t)CB * nqb * m);
+    unsigned char *flag = tf + (size_t)CB * nqb * m;  // nb * nqb flags
+    for (i64 b0 = 0; b0 < nb; b0 += CB) {
+        const i64 cb = nb - b0 < CB ? nb - b0 : CB;
+        SD_TRY(prof_begin(ctx, SD_PHASE_BD_MASKS));
+        bd_sig_rank_kernel<<<dim3((unsigned)ceil_div(n, 128), (unsigned)ceil_div(nqb, BM_SQ), (unsigned)cb), 128, 0,
+                             st>>>(Rp + b0 * TP * n, T, n, d_ql + b0 * nqb, (int)nqb, (int)W, Mw, sig, tf);
+        SD_TRY(prof_end(ctx));
+        SD_TRY(prof_begin(ctx, SD_PHASE_BD_PAIRS));
+        SD_TRY(launch_match(st, dim3((unsigned)nqb, (unsigned)cb), m, Mw, sig, tf, T, (int)W, d_out + b0 * nqb,
+                            flag + b0 * nqb));
+        SD_TRY(prof_end(ctx));
+        ctx->last.launches += 2;
+        SD_CUDA(cudaGetLastError());
+    }
+    // flagged queries -> enumerating kernels, matrix by matrix
+    std::vector<unsigned char> h_flag((size_t)(nb * nqb));
+    SD_CUDA(cudaMemcpyAsync(h_flag.data(), flag, h_flag.size(), cudaMemcpyDeviceToHost, st));
+    SD_CUDA(cudaStreamSynchronize(st));
+    std::vector<i64> pos;
+    for (i64 b = 0; b < nb; ++b) {
+        pos.clear();
+        for (i64 i = 0; i < nqb; ++i)
+            if (h_flag[(size_t)(b * nqb + i)]) pos.push_back(i);
+        if (pos.empty()) continue;
+        const i64 nf = (i64)pos.size();
+        SD_TRY(ctx->buf[BUF_SPLIT].reserve((size_t)nf * 3 * sizeof(i64)));
+        i64 *d_pos = ctx->buf[BUF_SPLIT].as<i64>();
+        i64 *d_qsub = d_pos + nf, *d_osub = d_qsub + nf;
+        SD_CUDA(cudaMemcpyAsync(d_pos, pos.data(), (size_t)nf * sizeof(i64), cudaMemcpyHostToDevice, st));
+        bm_gather_kernel<<<(unsigned)ceil_div(nf, 256), 256, 0, st>>>(d_ql + b * nqb, d_pos, nf, d_qsub);
+        ctx->last.launches++;
+        SD_CUDA(cudaStreamSynchronize(st));  // pos is a pageable host vector
+        SD_TRY(fallback(ctx, dXg + b * T * n, T, n, n, d_qsub, nf, d_osub));
+        bm_scatter_kernel<<<(unsigned)ceil_div(nf, 256), 256, 0, st>>>(d_osub, d_pos, nf, d_out + b * nqb);
+        ctx->last.launches++;
+        SD_CUDA(cudaGetLastError());
+    }
     return SD_OK;
 }
 

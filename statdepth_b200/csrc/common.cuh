@@ -134,6 +134,9 @@ bool bd_match_supported(i64 T, i64 n);
 int bd_strict_match_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const i64 *d_q, i64 nq, i64 *d_out,
                            int (*fallback)(sd_ctx *, const double *, i64, i64, i64, const i64 *, i64, i64 *),
                            i64 *n_fallback);
+int bd_strict_match_batched_device(sd_ctx *ctx, const double *dXg, i64 nb, i64 T, i64 n, const i64 *d_ql, i64 nqb,
+                                   i64 *d_out,
+                                   int (*fallback)(sd_ctx *, const double *, i64, i64, i64, const i64 *, i64, i64 *));
 int transpose_device(sd_ctx *ctx, const double *d_in, i64 rows, i64 cols, i64 ld_in, double *d_out);
 int gather_i64_device(sd_ctx *ctx, const i64 *d_src, const i64 *d_idx, i64 nq, i64 *d_out);
 int compact_columns_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, const i64 *d_cols, i64 m, double *d_out);

@@ -425,6 +425,12 @@ def test_k_sampled_and_batched(engine, oracle, golden):
                 loc = [int(np.searchsorted(members[b], g)) for g in qs[b]]
                 exp = oracle.mbd_counts_all(np.ascontiguousarray(Xm[:, members[b]]), j=j)[loc]
                 assert (got[b] == exp).all(), (b, j)
+        # strict: one rank pass + one signature / match launch pair for all batches; tied queries are re-enumerated
+        got = engine.band_depth_counts_batched(Xm, mem, qs, 2, False)
+        for b in range(B):
+            loc = [int(np.searchsorted(members[b], g)) for g in qs[b]]
+            exp = oracle.bd_counts(np.ascontiguousarray(Xm[:, members[b]]), loc)
+            assert (got[b] == exp).all(), b
 
 
 def test_reference_test_suite_types():
