@@ -68,7 +68,10 @@ enum sd_option {
     SD_OPT_BD_IMPL = 1,       /* enum sd_bd_impl */
     SD_OPT_MBD_FORCE_FALLBACK = 2, /* 1: rank every row with the generic (slow) path; testing aid */
     SD_OPT_PROFILE = 3,           /* 1: bracket every kernel phase with CUDA events (sd_get_phase_ns) */
-    SD_OPT_SIMPLICIAL_IMPL = 4    /* enum sd_simplicial_impl: 2-D triangle counting algorithm */
+    SD_OPT_SIMPLICIAL_IMPL = 4,   /* enum sd_simplicial_impl: 2-D triangle counting algorithm */
+    SD_OPT_ASYNC_DEVICE = 5       /* 1: sd_band_depth_f64_dev (relax = 1) only ENQUEUES its work on sd_stream() and
+                                     returns; status, timings and the result are valid after sd_sync().  Lets a caller
+                                     queue a collective behind the kernels without a host round trip. */
 };
 
 /* how 2-D simplicial counts (point clouds, relaxed multivariate simplex depth) are obtained */
@@ -124,6 +127,9 @@ int sd_get_phase_ns(sd_ctx *ctx, int64_t *out);
 int sd_probe_int8_peak(sd_ctx *ctx, double *ops_per_s);
 /* the context's cudaStream_t (as void*), so a caller can order its own work / events on it */
 void *sd_stream(sd_ctx *ctx);
+/* waits for everything queued on sd_stream(); with SD_OPT_ASYNC_DEVICE it completes the pending
+ * sd_band_depth_f64_dev call (returns its status, makes sd_get_timings valid) */
+int sd_sync(sd_ctx *ctx);
 
 /*
  * Univariate band depth numerators.  Replaces _univariate_band_depth (_functional.py:198-255)

@@ -17,7 +17,7 @@ STATUS_NAMES = {1: "SD_ERR_INVALID", 2: "SD_ERR_CUDA", 3: "SD_ERR_NO_DEVICE", 4:
                 5: "SD_ERR_OVERFLOW", 6: "SD_ERR_UNSUPPORTED"}
 LAYOUT_TN, LAYOUT_NT = 0, 1
 BD_AUTO, BD_BITS, BD_GEMM, BD_MATCH = 0, 1, 2, 3
-OPT_BD_IMPL, OPT_MBD_FORCE_FALLBACK, OPT_PROFILE, OPT_SIMPLICIAL_IMPL = 1, 2, 3, 4
+OPT_BD_IMPL, OPT_MBD_FORCE_FALLBACK, OPT_PROFILE, OPT_SIMPLICIAL_IMPL, OPT_ASYNC_DEVICE = 1, 2, 3, 4, 5
 SIMPLICIAL_AUTO, SIMPLICIAL_ENUMERATE, SIMPLICIAL_COUNT = 0, 1, 2
 PHASES = ("mbd_splitters", "mbd_partition", "mbd_rank", "mbd_generic", "bd_masks", "bd_pairs", "p6", "p7")
 
@@ -59,6 +59,7 @@ SIGNATURES = {
     "sd_get_phase_ns": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sd_probe_int8_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "sd_stream": (C.c_void_p, [C.c_void_p]),
+    "sd_sync": (C.c_int, [C.c_void_p]),
     "sd_band_depth_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p,
                                     C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "sd_band_depth_f64_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
@@ -166,6 +167,10 @@ class Engine:
 
     def stream(self) -> int:
         return int(self.lib.sd_stream(self._ctx) or 0)
+
+    def sync(self):
+        """Wait for the engine's stream; completes a call made under OPT_ASYNC_DEVICE (raises its error)."""
+        self._check(self.lib.sd_sync(self._ctx))
 
     @staticmethod
     def _queries(queries, n):

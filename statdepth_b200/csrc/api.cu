@@ -233,6 +233,10 @@ static int sd_band_depth_f64_dev_impl(sd_ctx *ctx, const double *dX, int64_t T, 
     SD_TRY(mark(ctx, 1));
     SD_TRY(band_depth_device(ctx, dX, T, n, ld, (const i64 *)d_query_idx, nq, j, relax, (i64 *)d_count_out));
     SD_TRY(mark(ctx, 2));
+    if (ctx->async_device && relax) {  // everything is queued on ctx->stream; sd_sync() completes the call
+        ctx->pending = 1;
+        return SD_OK;
+    }
     return end_call(ctx, false);
 }
 

@@ -99,6 +99,8 @@ struct sd_ctx {
     int mbd_force_fallback = 0;
     int profile = 0;
     int simplicial_impl = SD_SIMPLICIAL_AUTO;
+    int async_device = 0;   // SD_OPT_ASYNC_DEVICE
+    int pending = 0;        // an asynchronous device call has been queued and not yet completed by sd_sync()
     static const int MAX_PROF = 256;                 // event pairs per call when profiling
     cudaEvent_t prof_ev[2 * MAX_PROF] = {};          // created lazily
     int prof_phase[MAX_PROF] = {};

@@ -43,6 +43,10 @@ void DevBuf::release() {
 
 int begin_call(sd_ctx *ctx) {
     SD_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->pending) {  // an asynchronous call is still open: complete it (its events are about to be reused)
+        ctx->pending = 0;
+        SD_TRY(end_call(ctx, false));
+    }
     ctx->last = sd_timings{0, 0, 0, 0, 0, 0};
     ctx->prof_n = 0;
     for (int i = 0; i < SD_PHASE_COUNT; ++i) ctx->phase_ns[i] = 0;
@@ -306,6 +310,9 @@ int sd_set_option(sd_ctx *ctx, int option, int64_t value) {
             }
             ctx->simplicial_impl = (int)value;
             return SD_OK;
+        case SD_OPT_ASYNC_DEVICE:
+            ctx->async_device = value ? 1 : 0;
+            return SD_OK;
         default:
             sd::set_error("sd_set_option: unknown option %d", option);
             return SD_ERR_INVALID;
@@ -340,5 +347,19 @@ int sd_probe_int8_peak(sd_ctx *ctx, double *ops_per_s) {
 }
 
 void *sd_stream(sd_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int sd_sync(sd_ctx *ctx) {
+    if (!ctx) {
+        sd::set_error("sd_sync: NULL context");
+        return SD_ERR_INVALID;
+    }
+    SD_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->pending) {
+        ctx->pending = 0;
+        return sd::end_call(ctx, false);
+    }
+    SD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
 
 }  // extern "C"

@@ -213,6 +213,38 @@ def test_bd_randomized_differential(engine, oracle, seed):
         engine.set_option(OPT_BD_IMPL, BD_AUTO)
 
 
+def test_device_entry_point_async(engine, oracle):
+    """sd_band_depth_f64_dev on device buffers: synchronous by default; with SD_OPT_ASYNC_DEVICE it only enqueues and
+    sd_sync() completes the call -- result, timings and errors (a NaN in the input) all surface there."""
+    import torch
+    from statdepth_b200 import EngineError
+    from statdepth_b200._engine import OPT_ASYNC_DEVICE
+    X = walks(61, 40, 3000)
+    want = oracle.mbd_counts_all(X)
+    dX = torch.from_numpy(X).cuda()
+    out = torch.zeros(3000, dtype=torch.int64, device="cuda")
+    engine.band_depth_counts_dev(dX.data_ptr(), 40, 3000, 3000, out.data_ptr(), None, 3000, 2, True)
+    assert (out.cpu().numpy() == want).all()
+    try:
+        engine.set_option(OPT_ASYNC_DEVICE, 1)
+        out.zero_()
+        engine.band_depth_counts_dev(dX.data_ptr(), 40, 3000, 3000, out.data_ptr(), None, 3000, 2, True)
+        engine.sync()
+        assert (out.cpu().numpy() == want).all() and engine.timings()["kernel_ns"] > 0
+        # two calls back to back without a sync in between: the second call completes the first
+        engine.band_depth_counts_dev(dX.data_ptr(), 40, 3000, 3000, out.data_ptr(), None, 3000, 2, True)
+        engine.band_depth_counts_dev(dX.data_ptr(), 40, 3000, 3000, out.data_ptr(), None, 3000, 2, True)
+        engine.sync()
+        assert (out.cpu().numpy() == want).all()
+        dX[3, 77] = float("nan")
+        engine.band_depth_counts_dev(dX.data_ptr(), 40, 3000, 3000, out.data_ptr(), None, 3000, 2, True)  # queued
+        with pytest.raises(EngineError, match="NONFINITE"):
+            engine.sync()
+    finally:
+        engine.set_option(OPT_ASYNC_DEVICE, 0)
+        engine.sync()
+
+
 def test_mbd_heavy_parts_edge_cases(engine, oracle):
     """Parts over capacity: value tables (<= 8 distinct values per part, <= 128 such parts per row), -0.0 == +0.0,
     a mix of heavy classes and a continuous remainder, and the hand-over to the generic path beyond the limits."""
