@@ -23,12 +23,17 @@
 //                             exact fp64 compares on the values of X (gathered through the curve ids; rare),
 //                             and adds b(b-1) + a(a-1) to raw[curve] with a 64-bit RED.
 //      mbd_rank_big_kernel  : persistent; drains the work list of parts with 513..1024 values.
-//      mbd_heavy_kernel     : parts with more than CAP values hold a few heavily repeated values (ties):
-//                             ranked from a per-part table of at most 8 distinct values, no sorting.
+//      mbd_heavy_kernel     : one CTA per row, before the rank kernels: writes the exclusive prefix of the part
+//                             sizes (#values in lower parts) for them; rows with parts of more than CAP values
+//                             (a few heavily repeated values: ties) rank those parts from a per-part table of
+//                             at most 8 distinct values, no sorting.
 //   4. mbd_fallback_kernel  : rows in which a part of more than CAP values holds more than 8 distinct values
 //                             (adversarial spreads) are ranked by a generic one-CTA-per-row bitonic
-//                             sort of order-preserving u64 keys + binary-search ranks.  Correct for any
-//                             finite input; slower.
+//                             sort of order-preserving u64 keys + binary-search ranks (persistent over the rows:
+//                             almost always none is flagged).  Correct for any finite input; slower.
+//   5. mbd_finish_kernel    : numerator += rows * C(n-1,2) - raw / 2, once per call.
+// Row groups (mbd_all_device(..., group_rows)): the rows may be G stacked matrices of equal shape that accumulate
+// into [G][n] (batched permutations); rank-only calls (no accumulator) skip the REDs.
 // HBM layout: X[t*ld + c] float64 (time-major rows are contiguous and streamed with coalesced
 // loads); raw uint64[n] -> acc int64[n] (mbd_finish_kernel); part lists [row][part][CAP] float32 + uint32.
 #include <stdlib.h>
