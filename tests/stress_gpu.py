@@ -4,7 +4,7 @@ MBD cases against the CPU oracle; prints the number of mismatches (round 1: 0 of
 import sys, time
 import numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
-from statdepth_b200._engine import get_engine, BD_AUTO, BD_MATCH, BD_BITS, OPT_BD_IMPL
+from statdepth_b200._engine import get_engine, BD_AUTO, BD_MATCH, OPT_BD_IMPL
 from oracle import cpu_oracle as oracle
 from test_gpu_parity import _random_matrix
 oracle.build()
