@@ -380,17 +380,6 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_par
 // ---------------------------------------------------------------------------------------------
 // 3. per-part warp ranking
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_min(double v) {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, s));
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
-    return v;
-}
-
 struct RankOut {
     u64 *raw2;             // [n] sum over rows of b(b-1) + a(a-1); mbd_finish_kernel turns it into the j = 2 numerator
     i64 *acc3;             // j = 3 numerator, may be null
