@@ -76,9 +76,9 @@ enum sd_option {
 
 /* how 2-D simplicial counts (point clouds, relaxed multivariate simplex depth) are obtained */
 enum sd_simplicial_impl {
-    SD_SIMPLICIAL_AUTO = 0,      /* enumerate small samples (tolerance band honoured), count large ones */
+    SD_SIMPLICIAL_AUTO = 0,      /* enumerate samples of up to 64 points / curves, count larger ones (d = 2); same semantics */
     SD_SIMPLICIAL_ENUMERATE = 1, /* all (d+1)-subsets, closed simplex test with tolerance `tol` */
-    SD_SIMPLICIAL_COUNT = 2      /* O(n log n) angular counting, exact closed triangles (tol ignored), d = 2 */
+    SD_SIMPLICIAL_COUNT = 2      /* O(n log n) angular counting, d = 2: dist(p, triangle) <= tol; tol = 0: exact closed triangles */
 };
 
 /* phases of the modified-band-depth pipeline reported by sd_get_phase_ns */

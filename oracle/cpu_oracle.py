@@ -163,3 +163,33 @@ def oja(P, hull_volume, queries=None, pool=None):
     if rc:
         raise RuntimeError("sdo_oja rc=%d" % rc)
     return out
+
+
+def triangle_counts_arcs(P, queries=None, tol=1e-7):
+    """2-D simplicial numerator by O(n^2) arc counting (independent restatement of dist(p, triangle) <= tol)."""
+    P = _c64(P)
+    n, d = P.shape
+    assert d == 2
+    q = _q(queries, n)
+    out = np.zeros(q.size, dtype=np.int64)
+    rc = lib().sdo_triangle_counts_arcs(P.ctypes.data_as(_f64p), C.c_int64(n), C.c_int64(2), C.c_int64(1),
+                                        q.ctypes.data_as(_i64p), C.c_int64(q.size), C.c_double(tol),
+                                        out.ctypes.data_as(_i64p))
+    if rc:
+        raise RuntimeError("sdo_triangle_counts_arcs rc=%d" % rc)
+    return out
+
+
+def simplex2_relaxed_counts_arcs(F, queries=None, tol=1e-7):
+    """Relaxed multivariate simplex numerator (d = 2) by O(n^2) arc counting per (query, time point)."""
+    F = _c64(F)
+    N, T, d = F.shape
+    assert d == 2
+    q = _q(queries, N)
+    out = np.zeros(q.size, dtype=np.int64)
+    rc = lib().sdo_triangle_counts_arcs(F.ctypes.data_as(_f64p), C.c_int64(N), C.c_int64(2 * T), C.c_int64(T),
+                                        q.ctypes.data_as(_i64p), C.c_int64(q.size), C.c_double(tol),
+                                        out.ctypes.data_as(_i64p))
+    if rc:
+        raise RuntimeError("sdo_triangle_counts_arcs rc=%d" % rc)
+    return out

@@ -42,7 +42,7 @@ def _pointwisedepth(
             raise NotImplementedError('simplicial depth is implemented for d <= 3 on the B200 engine')
         q = _positions(to_compute, data.index, 'to_compute')
         tol = settings.get_simplex_tolerance()
-        if d != 2 or n <= 256:  # 2-D clouds above 256 points are counted, not enumerated
+        if d != 2 or n <= 64:  # 2-D clouds above 64 points are counted (tolerance band honoured), not enumerated
             settings.check_enumeration(float(len(q)) * binom(n - 1, d + 1), 'simplicial depth (d=%d, n=%d)' % (d, n))
         cnt = _dist.query_sharded(lambda qb: eng.simplicial_counts(P, qb, tol), q, np.int64)
         return pd.Series(index=to_compute, data=cnt.astype(np.float64) / binom(n, d + 1))

@@ -425,16 +425,22 @@ __global__ void mbd_finish_kernel(const u64 *__restrict__ raw2, i64 *__restrict_
 // value (tie-heavy data; any length) then costs O(1) per element; only a run that mixes distinct values
 // under one key is counted pairwise.  The part lists hold float offsets, so the EXACT values are read from
 // the row of X through the curve ids.  Kept out of line: it is rare and must not cost the sort registers.
-template <int EPL>
+// LINEAR: the sorted keys lie at skeys[pos] (sub-bin ranking) instead of the register-blocked layout.
+template <int EPL, bool LINEAR>
+__device__ __forceinline__ int run_at(const int pos) {
+    return LINEAR ? pos : (pos % EPL) * 32 + pos / EPL;
+}
+
+template <int EPL, bool LINEAR = false>
 __device__ __noinline__ void resolve_runs(const double *__restrict__ xrow, const u32 *__restrict__ pj, const int cnt,
                                           const u32 *skeys, u32 *sres, u32 *sflag, const int lane) {
     const int p0 = lane * EPL;
-    const u32 r_before = p0 > 0 && p0 <= cnt ? skeys[((p0 - 1) % EPL) * 32 + (p0 - 1) / EPL] >> 10 : 0xffffffffu;
+    const u32 r_before = p0 > 0 && p0 <= cnt ? skeys[run_at<EPL, LINEAR>(p0 - 1)] >> 10 : 0xffffffffu;
     int last_head = -1;  // last run start inside this lane's chunk
     u32 rp = r_before;
 #pragma unroll 1
     for (int i = 0; i < EPL && p0 + i < cnt; ++i) {
-        const u32 r = skeys[i * 32 + lane] >> 10;
+        const u32 r = skeys[run_at<EPL, LINEAR>(p0 + i)] >> 10;
         if (r != rp) last_head = p0 + i;
         rp = r;
     }
@@ -451,17 +457,17 @@ __device__ __noinline__ void resolve_runs(const double *__restrict__ xrow, const
 #pragma unroll 1
     for (int i = 0; i < EPL && p0 + i < cnt; ++i) {
         const int pos = p0 + i;
-        const u32 k = skeys[i * 32 + lane];
+        const u32 k = skeys[run_at<EPL, LINEAR>(p0 + i)];
         const u32 r = k >> 10;
         if (r != rp) rs = pos;
         rp = r;
-        const u32 rn = pos + 1 < cnt ? skeys[((pos + 1) % EPL) * 32 + (pos + 1) / EPL] >> 10 : 0xffffffffu;
+        const u32 rn = pos + 1 < cnt ? skeys[run_at<EPL, LINEAR>(pos + 1)] >> 10 : 0xffffffffu;
         u32 mark = rn != r ? (u32)(pos + 1 - rs) : 0u;  // run length, recorded by the run's last element
         if (rs != pos) {
-            const u32 k0 = skeys[(rs % EPL) * 32 + rs / EPL];
+            const u32 k0 = skeys[run_at<EPL, LINEAR>(rs)];
             if (!(xrow[pj[k & 1023u]] == xrow[pj[k0 & 1023u]])) mark |= 0x80000000u;  // the run holds distinct values
         }
-        if (mark) atomicOr(&sflag[(rs % EPL) * 32 + rs / EPL], mark);
+        if (mark) atomicOr(&sflag[run_at<EPL, LINEAR>(rs)], mark);
     }
     __syncwarp();
     rs = carry;
@@ -469,11 +475,11 @@ __device__ __noinline__ void resolve_runs(const double *__restrict__ xrow, const
 #pragma unroll 1
     for (int i = 0; i < EPL && p0 + i < cnt; ++i) {
         const int pos = p0 + i;
-        const u32 k = skeys[i * 32 + lane];
+        const u32 k = skeys[run_at<EPL, LINEAR>(p0 + i)];
         const u32 r = k >> 10;
         if (r != rp) rs = pos;
         rp = r;
-        const u32 f = sflag[(rs % EPL) * 32 + rs / EPL];
+        const u32 f = sflag[run_at<EPL, LINEAR>(rs)];
         const int len = (int)(f & 0x7fffffffu);
         if (len == 1) continue;  // not in a run: written by the caller's fast path
         const int slot = (int)(k & 1023u);
@@ -481,7 +487,7 @@ __device__ __noinline__ void resolve_runs(const double *__restrict__ xrow, const
         if (f & 0x80000000u) {  // mixed run: exact pairwise counting inside the run
             const double xs = xrow[pj[slot]];
             for (int m = rs; m < rs + len; ++m) {
-                const double xm = xrow[pj[skeys[(m % EPL) * 32 + m / EPL] & 1023u]];
+                const double xm = xrow[pj[skeys[run_at<EPL, LINEAR>(m)] & 1023u]];
                 less += xm < xs;
                 greater += xm > xs;
             }
@@ -491,6 +497,34 @@ __device__ __noinline__ void resolve_runs(const double *__restrict__ xrow, const
 }
 
 constexpr int EMIT_DEPTH = 4;
+
+// Emission of one ranked part in slot order (coalesced curve ids).  The RED's address waits for its id: a
+// one-at-a-time loop spent 40 % of the kernel's stall samples here, so EMIT_DEPTH ids are fetched a step ahead
+// (the caller fetched the first group under its sort).
+template <bool EXTRA>
+__device__ __forceinline__ void emit_part(const u32 *__restrict__ pj, const int cnt, const u32 base,
+                                          const i64 row_global, const RankOut &o, const u32 *sres, const int lane,
+                                          u32 (&jnext)[EMIT_DEPTH]) {
+    const u32 n32 = (u32)o.n;
+    const i64 acc_off = EXTRA ? acc_offset(o, row_global) : 0;  // grouped calls take the EXTRA instantiation
+#pragma unroll 1
+    for (int s0 = lane; s0 < cnt; s0 += 32 * EMIT_DEPTH) {
+        u32 j[EMIT_DEPTH], res[EMIT_DEPTH];
+#pragma unroll
+        for (int u = 0; u < EMIT_DEPTH; ++u) {
+            j[u] = jnext[u];
+            const int s = s0 + 32 * u;
+            res[u] = s < cnt ? sres[s] : 0u;
+            const int sn = s + 32 * EMIT_DEPTH;
+            jnext[u] = sn < cnt ? pj[sn] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < EMIT_DEPTH; ++u)
+            if (s0 + 32 * u < cnt)
+                emit_rank<EXTRA>(o, row_global, acc_off, j[u], base + (res[u] & 0xffffu), n32 - base - (res[u] >> 16));
+    }
+    __syncwarp();
+}
 
 // skeys / sres / sflag: this warp's shared scratch (CAP words each).
 // px: the part's values as float offsets from its reference splitter (monotone in x; equal offsets do NOT imply
@@ -502,7 +536,6 @@ __device__ __forceinline__ void rank_part(const float *__restrict__ px, const u3
                                           const double *__restrict__ xrow, const int cnt, const u32 base,
                                           const i64 row_global, const RankOut &o, u32 *skeys, u32 *sres, u32 *sflag,
                                           const int lane, float lo, float hi, const bool have_range) {
-    const u32 n32 = (u32)o.n;
     if (!have_range) {
         lo = INFINITY;
         hi = -INFINITY;
@@ -563,27 +596,119 @@ __device__ __forceinline__ void rank_part(const float *__restrict__ px, const u3
         resolve_runs<EPL>(xrow, pj, cnt, skeys, sres, sflag, lane);
     }
     __syncwarp();
-    // emission in slot order (coalesced curve ids).  The RED's address waits for its id: a one-at-a-time loop
-    // spent 40 % of the kernel's stall samples here, so EMIT_DEPTH ids are fetched a step ahead (the first
-    // group before the sort).
-    const i64 acc_off = EXTRA ? acc_offset(o, row_global) : 0;  // grouped calls take the EXTRA instantiation
+    emit_part<EXTRA>(pj, cnt, base, row_global, o, sres, lane, jnext);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3a. sub-bin ranking of a part of at most CAP/2 values (the common case): instead of a 512-wide sorting
+//     network over the warp (45 stages, 15 of them shuffles: 56 % of the old rank kernel's instructions),
+//     the 22-bit keys are counted into SB_BINS equal-width sub-bins of the part's range (the part spans one
+//     1/P quantile of the row, so its density is nearly flat and a bin holds cnt/64 +- a few values), a
+//     warp scan turns the counts into bin starts, the keys are scattered to their bins in shared memory, and
+//     every LANE sorts two whole bins of at most SB_CAP keys on its own registers with a 60-comparator
+//     network -- no shuffles, no selects, no padding of the part to a power of two.  Equal keys always share a
+//     bin, so runs (collisions / ties) are found by the sorting lane and resolved as before.  A part in which a
+//     bin overflows (tail parts with a decaying density, heavy ties) is handed to the work list of
+//     mbd_rank_big_kernel, whose full sorting network ranks any part.
+// ---------------------------------------------------------------------------------------------
+constexpr int SB_BINS = 64;   // two per lane
+constexpr int SB_CAP = 16;    // keys one lane sorts per bin
+constexpr int SB_EPL = CAP / 2 / 32;  // keys per lane when loading (16)
+static_assert(SB_EPL == 16 && SB_BINS == 64, "key >> 26 is the bin; pp[] packs 16 byte-sized positions");
+
+// returns false (warp-uniform, nothing emitted) when a bin holds more than SB_CAP keys
+template <bool EXTRA>
+__device__ __forceinline__ bool rank_part_subbin(const float *__restrict__ px, const u32 *__restrict__ pj,
+                                                 const double *__restrict__ xrow, const int cnt, const u32 base,
+                                                 const i64 row_global, const RankOut &o, u32 *skeys, u32 *sres,
+                                                 u32 *sflag, const int lane, float lo, float hi,
+                                                 const bool have_range) {
+    u32 *hist = sflag;  // [SB_BINS] counts, then bin starts (sflag proper is only needed by resolve_runs)
+    hist[lane] = 0u;
+    hist[lane + 32] = 0u;
+    if (!have_range) {
+        lo = INFINITY;
+        hi = -INFINITY;
 #pragma unroll 1
-    for (int s0 = lane; s0 < cnt; s0 += 32 * EMIT_DEPTH) {
-        u32 j[EMIT_DEPTH], res[EMIT_DEPTH];
-#pragma unroll
-        for (int u = 0; u < EMIT_DEPTH; ++u) {
-            j[u] = jnext[u];
-            const int s = s0 + 32 * u;
-            res[u] = s < cnt ? sres[s] : 0u;
-            const int sn = s + 32 * EMIT_DEPTH;
-            jnext[u] = sn < cnt ? pj[sn] : 0u;
+        for (int s = lane; s < cnt; s += 32) {
+            const float x = px[s];
+            lo = fminf(lo, x);
+            hi = fmaxf(hi, x);
         }
 #pragma unroll
-        for (int u = 0; u < EMIT_DEPTH; ++u)
-            if (s0 + 32 * u < cnt)
-                emit_rank<EXTRA>(o, row_global, acc_off, j[u], base + (res[u] & 0xffffu), n32 - base - (res[u] >> 16));
+        for (int d = 16; d > 0; d >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+        }
+    }
+    const float scale = (float)KEY_MAX / (hi - lo);  // see rank_part
+    u32 jnext[EMIT_DEPTH];
+#pragma unroll
+    for (int u = 0; u < EMIT_DEPTH; ++u) jnext[u] = lane + 32 * u < cnt ? pj[lane + 32 * u] : 0u;
+    __syncwarp();
+    u32 v[SB_EPL], pp[SB_EPL / 4];
+#pragma unroll
+    for (int k = 0; k < SB_EPL / 4; ++k) pp[k] = 0u;
+#pragma unroll
+    for (int k = 0; k < SB_EPL; ++k) {
+        const int s = lane + 32 * k;
+        u32 key = 0xffffffffu;
+        if (s < cnt) {
+            const u32 r = min((u32)__float2uint_rz((px[s] - lo) * scale), KEY_MAX);
+            key = (r << 10) | (u32)s;
+            const u32 pos = atomicAdd(&hist[r >> (KEY_BITS - 6)], 1u);  // arrival order inside the bin
+            pp[k >> 2] |= min(pos, 255u) << (8 * (k & 3));               // > SB_CAP overflows anyway
+        }
+        v[k] = key;
     }
     __syncwarp();
+    const u32 c0 = hist[2 * lane], c1 = hist[2 * lane + 1];
+    if (__any_sync(0xffffffffu, c0 > (u32)SB_CAP || c1 > (u32)SB_CAP)) return false;
+    u32 incl = c0 + c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    const u32 start0 = incl - c0 - c1;  // first sorted position of this lane's two bins
+    __syncwarp();
+    hist[2 * lane] = start0;
+    hist[2 * lane + 1] = start0 + c0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SB_EPL; ++k)
+        if (v[k] != 0xffffffffu) skeys[hist[v[k] >> 26] + ((pp[k >> 2] >> (8 * (k & 3))) & 255u)] = v[k];
+    __syncwarp();
+    bool any_run = false;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        const int start = (int)(h ? start0 + c0 : start0), c = (int)(h ? c1 : c0);
+        u32 w[SB_CAP];
+#pragma unroll
+        for (int i = 0; i < SB_CAP; ++i) w[i] = i < c ? skeys[start + i] : 0xffffffffu;
+        thread_sort16<u32>(w);
+#pragma unroll
+        for (int i = 0; i < SB_CAP; ++i) {
+            if (i < c) {
+                const u32 r = w[i] >> 10;
+                const bool left = i > 0 && (w[i > 0 ? i - 1 : 0] >> 10) == r;
+                const bool right = i + 1 < c && (w[i + 1 < SB_CAP ? i + 1 : i] >> 10) == r;
+                skeys[start + i] = w[i];  // sorted order, for resolve_runs
+                if (left || right) any_run = true;
+                else sres[w[i] & 1023u] = (u32)(start + i) | ((u32)(start + i + 1) << 16);
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, any_run)) {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < SB_EPL; ++k) sflag[lane + 32 * k] = 0u;
+        __syncwarp();
+        resolve_runs<SB_EPL, true>(xrow, pj, cnt, skeys, sres, sflag, lane);
+    }
+    __syncwarp();
+    emit_part<EXTRA>(pj, cnt, base, row_global, o, sres, lane, jnext);
+    return true;
 }
 
 constexpr int RANK_WARPS = 4;
@@ -645,6 +770,37 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_kernel(const Rank
     }
     if (cnt <= 256) rank_one<8, EXTRA>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
     else rank_one<16, EXTRA>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
+}
+
+// Same grid, sub-bin ranking (3a); parts it cannot rank (a bin overflows) join the big parts on the work list.
+template <bool EXTRA>
+__global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_subbin_kernel(const RankArgs a, const RankOut o) {
+    __shared__ u32 s_keys[RANK_WARPS][CAP / 2];
+    __shared__ u32 s_res[RANK_WARPS][CAP / 2];
+    __shared__ u32 s_flag[RANK_WARPS][CAP / 2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const i64 row = blockIdx.y;
+    const int part = blockIdx.x * RANK_WARPS + wid;
+    if (part >= a.P) return;
+    if (a.rowflag[row] & 2) return;
+    const int cnt = a.cursor[row * a.P + part];
+    if (cnt == 0 || cnt > CAP) return;
+    bool done = false;
+    if (cnt <= CAP / 2) {
+        const int P = a.P;
+        const u32 base = a.pbase[row * P + part];
+        const bool have_range = part > 0 && part < P - 1;
+        float hi = 0.f;
+        if (have_range) {
+            const float *sp = a.splitters_f + row * (P - 1);
+            hi = (float)((double)sp[part] - (double)sp[part - 1]);
+        }
+        const float *px = a.part_x + row * a.row_stride + (i64)part * CAP;
+        const u32 *pj = a.part_j + row * a.row_stride + (i64)part * CAP;
+        done = rank_part_subbin<EXTRA>(px, pj, a.X + row * a.ld, cnt, base, a.row0 + row, o, s_keys[wid], s_res[wid],
+                                       s_flag[wid], lane, 0.f, hi, have_range);
+    }
+    if (!done && lane == 0) a.biglist[atomicAdd(&a.bigcount[0], 1)] = make_int2((int)row, part);
 }
 
 // persistent: warps claim entries of the big-part work list
@@ -1011,6 +1167,8 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         const int v = atoi(e);
         if (v >= 64 && v <= 512) target = v;
     }
+    bool rank_subbin = true;  // SD_MBD_RANK=network selects the warp-wide sorting network (A/B aid)
+    if (const char *e = getenv("SD_MBD_RANK")) rank_subbin = strcmp(e, "network") != 0;
     int P = n <= CAP ? 1 : (int)ceil_div(n, target);  // n <= 1024: one part, one warp ranks the whole row
     if (P > MAX_PARTS) P = MAX_PARTS;
     int S = 0;
@@ -1108,10 +1266,12 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             const dim3 rgrid((unsigned)ceil_div(P, RANK_WARPS), (unsigned)rows);
             const unsigned bgrid = (unsigned)(ctx->sm_count * 4);
             if (o.acc3 || o.rank_b || o.group_rows) {
-                mbd_rank_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                if (rank_subbin) mbd_rank_subbin_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                else mbd_rank_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
                 mbd_rank_big_kernel<true><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
             } else {
-                mbd_rank_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                if (rank_subbin) mbd_rank_subbin_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                else mbd_rank_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
                 mbd_rank_big_kernel<false><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
             }
             SD_TRY(prof_end(ctx));

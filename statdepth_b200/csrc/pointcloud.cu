@@ -207,9 +207,9 @@ __global__ void __launch_bounds__(256) simplicial_kernel(const double *__restric
     if (threadIdx.x == 0) out[blockIdx.x] = (i64)tot;
 }
 
-// samples up to this size are enumerated (reference semantics incl. the tolerance band); larger 2-D
-// samples are counted in O(n log n) per query (simplicial_count.cu)
-constexpr i64 SIMPLICIAL_ENUM_MAX_N = 256;
+// samples up to this size are enumerated; larger 2-D samples are counted in O(n log n) per query
+// (simplicial_count.cu).  Both honour the tolerance band `tol` of the reference's LP.
+constexpr i64 SIMPLICIAL_ENUM_MAX_N = 64;
 constexpr i64 SIMPLEX_ENUM_MAX_N = 64;
 
 int simplicial_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 nq, double tol,
@@ -217,7 +217,7 @@ int simplicial_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_
     if (nq == 0) return SD_OK;
     if (d == 2 && (ctx->simplicial_impl == SD_SIMPLICIAL_COUNT ||
                    (ctx->simplicial_impl == SD_SIMPLICIAL_AUTO && n > SIMPLICIAL_ENUM_MAX_N)))
-        return simplicial2_count_device(ctx, dP, n, 2, 1, d_q, nq, d_out);
+        return simplicial2_count_device(ctx, dP, n, 2, 1, d_q, nq, tol, d_out);
     cudaStream_t st = ctx->stream;
     const unsigned grid = (unsigned)nq;
     switch (d) {
@@ -340,7 +340,7 @@ int simplex_depth_device(sd_ctx *ctx, const double *dF, i64 N, i64 T, int d, con
     // relaxed depth is a sum over time points of triangle counts: countable per (query, time point)
     if (d == 2 && relax && (ctx->simplicial_impl == SD_SIMPLICIAL_COUNT ||
                             (ctx->simplicial_impl == SD_SIMPLICIAL_AUTO && N > SIMPLEX_ENUM_MAX_N)))
-        return simplicial2_count_device(ctx, dF, N, 2 * T, T, d_q, nq, d_out);
+        return simplicial2_count_device(ctx, dF, N, 2 * T, T, d_q, nq, tol, d_out);
     cudaStream_t st = ctx->stream;
     const unsigned grid = (unsigned)nq;
     switch (d) {

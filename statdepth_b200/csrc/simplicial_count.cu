@@ -17,9 +17,23 @@
 // Ranks come from the modified-band-depth rank pipeline (mbd.cu), run on two key matrices per batch of
 // instances: A = keys (n per row), B = keys and antipodes (2n per row).
 //
-// Semantics: exact closed triangles of the computed float64 directions (tolerance 0).  The reference
-// decides with an LP whose ~1e-7 feasibility band only matters for triangles with p within 1e-7 of an
-// edge; the enumeration kernels (pointcloud.cu) keep that band for the sizes the reference can run.
+// Semantics.  tol == 0: exact closed triangles of the computed float64 directions (keys above).
+// tol > 0 (the default, 1e-7): the reference decides with an LP (scipy.optimize.linprog, _containment.py:164-176)
+// whose feasibility band accepts p up to ~1e-7 OUTSIDE a triangle, and its own multivariate fixture consists of
+// collinear triples only (testing/_generating.py:94-96), so that band decides every one of them.  The
+// enumeration kernels restate the LP as dist(p, triangle) <= tol (simplex_pred.cuh); the counting form of the
+// same predicate: a triangle MISSES the closed disk D(p, tol) iff a tangent line of the disk has all three
+// vertices strictly beyond it, i.e. iff the three open arcs
+//     A_i = (phi_i - alpha_i, phi_i + alpha_i),  phi_i = angle of x_i - p,  alpha_i = acos(tol / |x_i - p|) < pi/2
+// of tangent directions have a common point (points within tol of p have no arc: every triangle through them
+// meets the disk).  Arcs are shorter than pi, so a non-empty common intersection is one arc whose start is
+// the start s_i of exactly one class of arcs with equal start, and
+//     #missing = sum over classes [C(g + c, 3) - C(c, 3)],   c = #{other arcs that contain s_i}
+//              c = #{s_j < s_i} - #{e_j <= s_i} + #{arcs that wrap past 2 pi}      (e_j taken mod 2 pi)
+// -- again two rank passes (starts; starts and ends) through the K1 pipeline.  With tol = 0 the arcs are
+// the open half-turns of the exact formula.  Angles here come from atan2 / acos (a few ulp): decisions can
+// differ from the enumeration predicate only for triangles whose distance to p is within ~1e-15 |x - p| of
+// tol, far inside the documented tie band of the LP itself (DESIGN.md "Oracle and parity").
 #include "common.cuh"
 
 namespace sd {
@@ -60,11 +74,18 @@ __device__ __forceinline__ double sc_key(double dx, double dy) {
         if (ax < dy) { oct = 2.0; f = ax / dy; }            // [pi/2, 3pi/4)
         else         { oct = 3.0; f = 1.0 - dy / ax; }      // [3pi/4, pi)
     }
-    return (add + oct) + f;  // f in [0,1): one rounding to the [8,16) binade, monotone
+    // f in [0,1): one rounding to the [8,16) binade, monotone.  A direction a hair below the +x axis
+    // (f = 1 - tiny rounds to 1, or 15 + f rounds up) would land on 16.0, the value range of the sentinels:
+    // angle 2 pi IS angle 0, so it folds back onto 8.0 (its antipode is then exactly 12.0).
+    const double k = (add + oct) + f;
+    return k >= 16.0 ? 8.0 : k;
 }
 
-// KA[i][j] = key_j; KB[i][j] = key_j, KB[i][n + j] = antipode of key_j
-__global__ void __launch_bounds__(256) sc_keys_kernel(const ScGeom g, const i64 n, const i64 ninst,
+constexpr double SC_TWO_PI = 6.283185307179586476925286766559;
+
+// KA[i][j] = key_j; KB[i][j] = key_j, KB[i][n + j] = antipode of key_j.
+// tol > 0: key_j = start of arc j in [0, 2 pi], second half of KB = its end mod 2 pi (sentinels as for tol = 0).
+__global__ void __launch_bounds__(256) sc_keys_kernel(const ScGeom g, const i64 n, const i64 ninst, const double tol,
                                                       double *__restrict__ KA, double *__restrict__ KB,
                                                       int *__restrict__ status) {
     const i64 li = blockIdx.y;  // instance within the batch
@@ -84,6 +105,19 @@ __global__ void __launch_bounds__(256) sc_keys_kernel(const ScGeom g, const i64 
             const double dx = xj - px, dy = yj - py;
             if (dx == 0.0 && dy == 0.0) {
                 u = w = SC_ZERO;
+            } else if (tol > 0.0) {
+                const double r = hypot(dx, dy);
+                if (r <= tol) {
+                    u = w = SC_ZERO;  // within the band of p: every triangle through this point meets the disk
+                } else {
+                    double phi = atan2(dy, dx);
+                    if (phi < 0.0) phi += SC_TWO_PI;
+                    const double alpha = acos(tol / r);
+                    u = phi - alpha;
+                    if (u < 0.0) u += SC_TWO_PI;
+                    w = u + 2.0 * alpha;
+                    if (w >= SC_TWO_PI) w -= SC_TWO_PI;  // the arc wraps: its end lies below its start
+                }
             } else {
                 u = sc_key(dx, dy);
                 w = u < 12.0 ? u + 4.0 : u - 4.0;  // exact: same binade
@@ -98,25 +132,29 @@ __global__ void __launch_bounds__(256) sc_keys_kernel(const ScGeom g, const i64 
 
 __device__ __forceinline__ i64 c3(i64 m) { return m < 3 ? 0 : (m * (m - 1) / 2) * (m - 2) / 3; }
 
-// one CTA per instance.  bA/aA: ranks of row A; bB: ranks (strictly below) of row B.
-// out[query slot] += #triangles of other points containing the query point.
+// one CTA per instance.  bA/aA: ranks of row A; bB/aB: ranks (strictly below / above) of row B.
+// out[query slot] += #triangles of other points containing the query point (ARCS: meeting the disk D(p, tol)).
+template <bool ARCS>
 __global__ void __launch_bounds__(256) sc_reduce_kernel(const ScGeom g, const i64 n, const double *__restrict__ KA,
+                                                        const double *__restrict__ KB,
                                                         const int *__restrict__ bA, const int *__restrict__ aA,
-                                                        const int *__restrict__ bB, int *__restrict__ claim,
-                                                        i64 *__restrict__ out) {
+                                                        const int *__restrict__ bB, const int *__restrict__ aB,
+                                                        int *__restrict__ claim, i64 *__restrict__ out) {
     __shared__ i64 s_red[8];
     __shared__ i64 s_cnt[2];
     const i64 li = blockIdx.x;
     const i64 inst = g.inst0 + li;
     const double *ka = KA + li * n;
-    const int *ba = bA + li * n, *aa = aA + li * n, *bb = bB + li * 2 * n;
+    const int *ba = bA + li * n, *aa = aA + li * n, *bb = bB + li * 2 * n, *ab = aB + li * 2 * n;
     int *cl = claim + li * n;
-    // pass 1: number of real directions m' and how many of them lie in [0, pi)  (key < 12)
+    // pass 1: number of real directions m' and how many of them lie in [0, pi)  (key < 12);
+    // ARCS: `low` counts the arcs that wrap past 2 pi (end below start)
     i64 real = 0, low = 0;
     for (i64 j = threadIdx.x; j < n; j += blockDim.x) {
         const double u = ka[j];
         real += u < 16.0;
-        low += u < 12.0;
+        if (ARCS) low += u < 16.0 && KB[li * 2 * n + n + j] < u;
+        else low += u < 12.0;
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
@@ -138,12 +176,16 @@ __global__ void __launch_bounds__(256) sc_reduce_kernel(const ScGeom g, const i6
         if (!(u < 16.0)) continue;  // zero vector or the query itself
         const i64 L = ba[j];                      // real directions strictly before this one
         const i64 gsz = n - L - (i64)aa[j];       // size of its class (sentinels are never equal to it)
-        const i64 b2w = bb[n + j];                // entries of row B strictly below the antipode
         i64 c;
-        if (u < 12.0) {
+        if (ARCS) {
+            // #{starts < s} - #{ends <= s} + #wrapping, #{ends <= s} = #{B <= s} - #{A <= s}
+            c = L - ((2 * n - (i64)ab[j]) - (n - (i64)aa[j])) + L4;
+        } else if (u < 12.0) {
+            const i64 b2w = bb[n + j];            // entries of row B strictly below the antipode
             const i64 Lw = b2w - L - H;           // real directions strictly before the antipode
             c = Lw - L - gsz;
         } else {
+            const i64 b2w = bb[n + j];
             const i64 Lw = b2w - L + L4;
             c = (mreal - L - gsz) + Lw;
         }
@@ -167,7 +209,7 @@ __global__ void __launch_bounds__(256) sc_reduce_kernel(const ScGeom g, const i6
 
 // Counts for `nq` queries x `T` instances each (T = 1 for point clouds).  d_out[nq] is zeroed here.
 int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride_j, i64 T, const i64 *d_q, i64 nq,
-                             i64 *d_out) {
+                             double tol, i64 *d_out) {
     cudaStream_t st = ctx->stream;
     SD_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nq * sizeof(i64), st));
     const i64 ninst_total = nq * T;
@@ -176,19 +218,24 @@ int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride
         set_error("simplicial counting: n=%lld too large", (long long)n);
         return SD_ERR_UNSUPPORTED;
     }
-    // batch size: ~44 n bytes of keys and ranks per instance (+ the rank pipeline's part lists)
-    i64 IB = (i64)((3ull << 30) / (size_t)(48 * n));
+    if (!(tol >= 0.0)) {
+        set_error("simplicial counting: tolerance %g is negative or NaN", tol);
+        return SD_ERR_INVALID;
+    }
+    // batch size: ~52 n bytes of keys and ranks per instance (+ the rank pipeline's part lists)
+    i64 IB = (i64)((3ull << 30) / (size_t)(56 * n));
     if (IB < 1) IB = 1;
     if (IB > 32768) IB = 32768;
     if (IB > ninst_total) IB = ninst_total;
     SD_TRY(ctx->buf[BUF_IN2].reserve((size_t)IB * n * 3 * sizeof(double)));
-    SD_TRY(ctx->buf[BUF_MASK].reserve((size_t)IB * n * 5 * sizeof(int)));
+    SD_TRY(ctx->buf[BUF_MASK].reserve((size_t)IB * n * 7 * sizeof(int)));
     double *KA = ctx->buf[BUF_IN2].as<double>();
     double *KB = KA + (size_t)IB * n;
     int *bA = ctx->buf[BUF_MASK].as<int>();
     int *aA = bA + (size_t)IB * n;
     int *bB = aA + (size_t)IB * n;
-    int *claim = bB + (size_t)IB * 2 * n;  // the 'above' ranks of the doubled matrix are not needed
+    int *aB = bB + (size_t)IB * 2 * n;
+    int *claim = aB + (size_t)IB * 2 * n;
     ScGeom g;
     g.pts = d_pts;
     g.stride_j = stride_j;
@@ -203,12 +250,13 @@ int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride
             set_error("simplicial counting: internal batch too large");
             return SD_ERR_UNSUPPORTED;
         }
-        sc_keys_kernel<<<dim3(gx, (unsigned)ni), 256, 0, st>>>(g, n, ni, KA, KB, ctx->d_status);
+        sc_keys_kernel<<<dim3(gx, (unsigned)ni), 256, 0, st>>>(g, n, ni, tol, KA, KB, ctx->d_status);
         ctx->last.launches++;
         SD_CUDA(cudaMemsetAsync(claim, 0, (size_t)ni * n * sizeof(int), st));
         SD_TRY(mbd_all_device(ctx, KA, ni, n, n, false, nullptr, nullptr, bA, aA));  // ranks only
-        SD_TRY(mbd_all_device(ctx, KB, ni, 2 * n, 2 * n, false, nullptr, nullptr, bB, nullptr));
-        sc_reduce_kernel<<<(unsigned)ni, 256, 0, st>>>(g, n, KA, bA, aA, bB, claim, d_out);
+        SD_TRY(mbd_all_device(ctx, KB, ni, 2 * n, 2 * n, false, nullptr, nullptr, bB, tol > 0.0 ? aB : nullptr));
+        if (tol > 0.0) sc_reduce_kernel<true><<<(unsigned)ni, 256, 0, st>>>(g, n, KA, KB, bA, aA, bB, aB, claim, d_out);
+        else sc_reduce_kernel<false><<<(unsigned)ni, 256, 0, st>>>(g, n, KA, KB, bA, aA, bB, aB, claim, d_out);
         ctx->last.launches++;
         SD_CUDA(cudaGetLastError());
     }

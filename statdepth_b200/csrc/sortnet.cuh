@@ -79,4 +79,23 @@ __device__ __forceinline__ void warp_bitonic_sort(K (&v)[EPL], const int lane) {
     }
 }
 
+// 16 keys of ONE thread, 60 compare-exchanges in 10 layers (a minimal-size 16-input network; checked with the
+// 0-1 principle over all 65536 inputs).  The sub-bin ranking of mbd.cu sorts its bins of <= 16 keys with it:
+// every compare-exchange works on the thread's own registers, so there are no shuffles and no selects.
+template <typename K>
+__device__ __forceinline__ void thread_sort16(K (&w)[16]) {
+#define SD_CE(a, b) ce_key(w[a], w[b])
+    SD_CE(0, 13); SD_CE(1, 12); SD_CE(2, 15); SD_CE(3, 14); SD_CE(4, 8); SD_CE(5, 6); SD_CE(7, 11); SD_CE(9, 10);
+    SD_CE(0, 5); SD_CE(1, 7); SD_CE(2, 9); SD_CE(3, 4); SD_CE(6, 13); SD_CE(8, 14); SD_CE(10, 15); SD_CE(11, 12);
+    SD_CE(0, 1); SD_CE(2, 3); SD_CE(4, 5); SD_CE(6, 8); SD_CE(7, 9); SD_CE(10, 11); SD_CE(12, 13); SD_CE(14, 15);
+    SD_CE(0, 2); SD_CE(1, 3); SD_CE(4, 10); SD_CE(5, 11); SD_CE(6, 7); SD_CE(8, 9); SD_CE(12, 14); SD_CE(13, 15);
+    SD_CE(1, 2); SD_CE(3, 12); SD_CE(4, 6); SD_CE(5, 7); SD_CE(8, 10); SD_CE(9, 11); SD_CE(13, 14);
+    SD_CE(1, 4); SD_CE(2, 6); SD_CE(5, 8); SD_CE(7, 10); SD_CE(9, 13); SD_CE(11, 14);
+    SD_CE(2, 4); SD_CE(3, 6); SD_CE(9, 12); SD_CE(11, 13);
+    SD_CE(3, 5); SD_CE(6, 8); SD_CE(7, 9); SD_CE(10, 12);
+    SD_CE(3, 4); SD_CE(5, 6); SD_CE(7, 8); SD_CE(9, 10); SD_CE(11, 12);
+    SD_CE(6, 7); SD_CE(8, 9);
+#undef SD_CE
+}
+
 }  // namespace sd
