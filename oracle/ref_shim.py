@@ -17,7 +17,9 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("STATDEPTH_REFERENCE", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # oracle/make_ref.sh (travels to the GPU box)
+REFERENCE_ROOT = os.environ.get("STATDEPTH_REFERENCE",
+                                "/root/reference" if os.path.isdir("/root/reference/statdepth") else _STAGED)
 
 
 def available() -> bool:

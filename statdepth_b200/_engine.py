@@ -296,6 +296,11 @@ def get_engine(device: int = None) -> Engine:
     """Process-wide engine for `device` (default: $LOCAL_RANK or $STATDEPTH_DEVICE or 0)."""
     if device is None:
         device = int(os.environ.get("STATDEPTH_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        if "STATDEPTH_DEVICE" not in os.environ:
+            # LOCAL_RANK is out of range when CUDA_VISIBLE_DEVICES is narrowed to one device per rank
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis is not None and device >= len([v for v in vis.split(",") if v.strip()]):
+                device = 0
     eng = _engines.get(device)
     if eng is None:
         eng = Engine(device)

@@ -46,7 +46,7 @@ def _univariate_depths(X: np.ndarray, queries, J: int, relax: bool) -> np.ndarra
     for j in range(2, J + 1):
         if j <= 3:
             if relax:
-                cnt = _dist.relaxed_counts(lambda Xr, q, jj: eng.band_depth_counts(Xr, q, jj, True), X, queries, j)
+                cnt = _dist.relaxed_counts(lambda Xr, q, jj: eng.band_depth_counts(Xr, q, jj, True), X, queries, j, eng)
             else:
                 qs = np.arange(n, dtype=np.int64) if queries is None else np.asarray(queries, dtype=np.int64)
                 cnt = _dist.query_sharded(lambda qb: eng.band_depth_counts(X, qb, j, False), qs, np.int64)

@@ -68,7 +68,9 @@ def _pointwisedepth(
         q = _positions(idx, data.index, 'to_compute')
         # reference quirk (:182-183,191-193): with to_compute the subsets are drawn from to_compute only
         pool = None if to_compute is None else q
-        settings.check_enumeration(float(len(q)) * binom(n if pool is None else len(pool), d), 'Oja depth (d=%d)' % d)
+        npool = n if pool is None else len(pool)
+        if d != 2 or npool <= 256:  # 2-D pools above 256 points are summed in O(n log n) per query, not enumerated
+            settings.check_enumeration(float(len(q)) * binom(npool, d), 'Oja depth (d=%d)' % d)
         vals = _dist.query_sharded(lambda qb: eng.oja(P, hull_volume, qb, pool), q, np.float64)
         # reference quirk (:205): index=to_compute, i.e. a default RangeIndex when to_compute is None
         return pd.Series(index=to_compute, data=vals)

@@ -151,6 +151,8 @@ int simplicial_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_
                       i64 *d_out);
 int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride_j, i64 T, const i64 *d_q, i64 nq,
                              double tol, i64 *d_out);
+int oja2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, const i64 *d_q, i64 nq, double hull_volume,
+                      double *d_out);
 int simplex_depth_device(sd_ctx *ctx, const double *dF, i64 N, i64 T, int d, const i64 *d_q, i64 nq,
                          int relax, double tol, i64 *d_out);
 

@@ -241,7 +241,7 @@ int sd_init(int device, sd_ctx **out) {
     SD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) SD_CUDA(cudaEventCreateWithFlags(&ctx->ev_pipe[i], cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) SD_CUDA(cudaEventCreate(&ctx->ev[i]));
-    SD_CUDA(cudaMalloc(&ctx->d_status, 4 * sizeof(int)));
+    SD_CUDA(cudaMalloc(&ctx->d_status, 8 * sizeof(int)));
     SD_CUDA(cudaMallocHost(&ctx->h_status, 4 * sizeof(int)));
     memset(ctx->h_status, 0, 4 * sizeof(int));
     *out = ctx;

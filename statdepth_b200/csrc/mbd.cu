@@ -602,19 +602,24 @@ __device__ __forceinline__ void rank_part(const float *__restrict__ px, const u3
 // ---------------------------------------------------------------------------------------------
 // 3a. sub-bin ranking of a part of at most CAP/2 values (the common case): instead of a 512-wide sorting
 //     network over the warp (45 stages, 15 of them shuffles: 56 % of the old rank kernel's instructions),
-//     the 22-bit keys are counted into SB_BINS equal-width sub-bins of the part's range (the part spans one
+//     the 22-bit keys are counted into 64 (128 for parts of 513..1024 values) equal-width sub-bins of the part's range (the part spans one
 //     1/P quantile of the row, so its density is nearly flat and a bin holds cnt/64 +- a few values), a
 //     warp scan turns the counts into bin starts, the keys are scattered to their bins in shared memory, and
-//     every LANE sorts two whole bins of at most SB_CAP keys on its own registers with a 60-comparator
+//     every LANE sorts its two (four) whole bins of at most SB_CAP keys on its own registers with a 60-comparator
 //     network -- no shuffles, no selects, no padding of the part to a power of two.  Equal keys always share a
 //     bin, so runs (collisions / ties) are found by the sorting lane and resolved as before.  A part in which a
 //     bin overflows (tail parts with a decaying density, heavy ties) is handed to the work list of
 //     mbd_rank_big_kernel, whose full sorting network ranks any part.
 // ---------------------------------------------------------------------------------------------
-constexpr int SB_BINS = 64;   // two per lane
 constexpr int SB_CAP = 16;    // keys one lane sorts per bin
-constexpr int SB_EPL = CAP / 2 / 32;  // keys per lane when loading (16)
-static_assert(SB_EPL == 16 && SB_BINS == 64 && KEY_BITS == 22, "key >> 26 is the bin");
+// EPL keys per lane when loading (16: parts of up to 512 values, 32: up to 1024); EPL / 8 bins per lane, so a
+// bin holds a quarter of its capacity on average when the part is full
+template <int EPL> struct SubBin {
+    static constexpr int BPL = EPL / 8;           // bins per lane (2 or 4)
+    static constexpr int BINS = 32 * BPL;         // 64 or 128
+    static constexpr int SHIFT = EPL == 16 ? 26 : 25;  // packed key >> SHIFT = bin (22 key bits above 10 slot bits)
+};
+static_assert(KEY_BITS == 22, "SubBin::SHIFT assumes 22-bit keys over 10 slot bits");
 
 // One lane sorts bin [start, start + c) of skeys on its registers and records the final position of every key that
 // shares its 22-bit key with no neighbour (sres[slot] = pos | (pos + 1) << 16); returns whether a run of equal keys
@@ -643,32 +648,44 @@ __device__ __forceinline__ bool subbin_sort_bin(u32 *skeys, u32 *sres, const int
     return any_run;
 }
 
+// bin b of this lane starts at start0 + (counts of the lane's earlier bins, packed one byte each in cpack)
+__device__ __forceinline__ int subbin_start(const int start0, const u32 cpack, const int b) {
+    int s = start0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < b) s += (int)((cpack >> (8 * k)) & 255u);
+    return s;
+}
+
+template <int EPL>
 __device__ __noinline__ void subbin_resolve(const double *__restrict__ xrow, const u32 *__restrict__ pj, const int cnt,
                                             u32 *skeys, u32 *sres, u32 *sflag, const int lane, const int start0,
-                                            const int c0, const int c1) {
+                                            const u32 cpack) {
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) subbin_sort_bin<true>(skeys, sres, h ? start0 + c0 : start0, h ? c1 : c0);
+    for (int b = 0; b < SubBin<EPL>::BPL; ++b)
+        subbin_sort_bin<true>(skeys, sres, subbin_start(start0, cpack, b), (int)((cpack >> (8 * b)) & 255u));
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < SB_EPL; ++k) sflag[lane + 32 * k] = 0u;
+    for (int k = 0; k < EPL; ++k) sflag[lane + 32 * k] = 0u;
     __syncwarp();
-    resolve_runs<SB_EPL, true>(xrow, pj, cnt, skeys, sres, sflag, lane);
+    resolve_runs<EPL, true>(xrow, pj, cnt, skeys, sres, sflag, lane);
 }
 
 // returns false (warp-uniform, nothing emitted) when a bin holds more than SB_CAP keys
-template <bool EXTRA>
+template <int EPL, bool EXTRA>
 __device__ __forceinline__ bool rank_part_subbin(const float *__restrict__ px, const u32 *__restrict__ pj,
                                                  const double *__restrict__ xrow, const int cnt, const u32 base,
                                                  const i64 row_global, const RankOut &o, u32 *skeys, u32 *sres,
                                                  u32 *sflag, const int lane, float lo, float hi,
                                                  const bool have_range) {
-    u32 *hist = sflag;  // [SB_BINS] counts, then bin cursors (sflag proper is only needed by resolve_runs)
-    hist[lane] = 0u;
-    hist[lane + 32] = 0u;
-    // all loads of the part first: an atomic between two loads would serialise their latencies
-    float xv[SB_EPL];
+    typedef SubBin<EPL> SB;
+    u32 *hist = sflag;  // [BINS] counts, then bin cursors (sflag proper is only needed by resolve_runs)
 #pragma unroll
-    for (int k = 0; k < SB_EPL; ++k) xv[k] = lane + 32 * k < cnt ? px[lane + 32 * k] : 0.f;
+    for (int b = 0; b < SB::BPL; ++b) hist[lane + 32 * b] = 0u;
+    // all loads of the part first: an atomic between two loads would serialise their latencies
+    float xv[EPL];
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) xv[k] = lane + 32 * k < cnt ? px[lane + 32 * k] : 0.f;
     u32 jnext[EMIT_DEPTH];
 #pragma unroll
     for (int u = 0; u < EMIT_DEPTH; ++u) jnext[u] = lane + 32 * u < cnt ? pj[lane + 32 * u] : 0u;
@@ -676,7 +693,7 @@ __device__ __forceinline__ bool rank_part_subbin(const float *__restrict__ px, c
         lo = INFINITY;
         hi = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < SB_EPL; ++k)
+        for (int k = 0; k < EPL; ++k)
             if (lane + 32 * k < cnt) {
                 lo = fminf(lo, xv[k]);
                 hi = fmaxf(hi, xv[k]);
@@ -689,42 +706,50 @@ __device__ __forceinline__ bool rank_part_subbin(const float *__restrict__ px, c
     }
     const float scale = (float)KEY_MAX / (hi - lo);  // see rank_part
     __syncwarp();
-    u32 v[SB_EPL];
+    u32 v[EPL];
 #pragma unroll
-    for (int k = 0; k < SB_EPL; ++k) {
+    for (int k = 0; k < EPL; ++k) {
         const int s = lane + 32 * k;
         u32 key = 0xffffffffu;
         if (s < cnt) {
             const u32 r = min((u32)__float2uint_rz((xv[k] - lo) * scale), KEY_MAX);
             key = (r << 10) | (u32)s;
-            atomicAdd(&hist[r >> (KEY_BITS - 6)], 1u);
+            atomicAdd(&hist[key >> SB::SHIFT], 1u);
         }
         v[k] = key;
     }
     __syncwarp();
-    const u32 c0 = hist[2 * lane], c1 = hist[2 * lane + 1];
-    if (__any_sync(0xffffffffu, c0 > (u32)SB_CAP || c1 > (u32)SB_CAP)) return false;
-    u32 incl = c0 + c1;
+    u32 cpack = 0u, tot = 0u;  // this lane's bin counts, one byte each
+    bool over = false;
+#pragma unroll
+    for (int b = 0; b < SB::BPL; ++b) {
+        const u32 c = hist[SB::BPL * lane + b];
+        over |= c > (u32)SB_CAP;
+        cpack |= min(c, 255u) << (8 * b);
+        tot += c;
+    }
+    if (__any_sync(0xffffffffu, over)) return false;
+    u32 incl = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const u32 up = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += up;
     }
-    const u32 start0 = incl - c0 - c1;  // first sorted position of this lane's two bins
-    __syncwarp();
-    hist[2 * lane] = start0;
-    hist[2 * lane + 1] = start0 + c0;
+    const int start0 = (int)(incl - tot);  // first sorted position of this lane's bins
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < SB_EPL; ++k)
-        if (v[k] != 0xffffffffu) skeys[atomicAdd(&hist[v[k] >> 26], 1u)] = v[k];  // any order inside the bin
+    for (int b = 0; b < SB::BPL; ++b) hist[SB::BPL * lane + b] = (u32)subbin_start(start0, cpack, b);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < EPL; ++k)
+        if (v[k] != 0xffffffffu) skeys[atomicAdd(&hist[v[k] >> SB::SHIFT], 1u)] = v[k];  // any order inside the bin
     __syncwarp();
     bool any_run = false;
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h)  // rolled: one copy of the 60-comparator network in the instruction cache
-        any_run |= subbin_sort_bin<false>(skeys, sres, (int)(h ? start0 + c0 : start0), (int)(h ? c1 : c0));
+    for (int b = 0; b < SB::BPL; ++b)  // rolled: one copy of the 60-comparator network in the instruction cache
+        any_run |= subbin_sort_bin<false>(skeys, sres, subbin_start(start0, cpack, b), (int)((cpack >> (8 * b)) & 255u));
     if (__any_sync(0xffffffffu, any_run))  // rare: publish the sorted keys and resolve the runs exactly
-        subbin_resolve(xrow, pj, cnt, skeys, sres, sflag, lane, (int)start0, (int)c0, (int)c1);
+        subbin_resolve<EPL>(xrow, pj, cnt, skeys, sres, sflag, lane, start0, cpack);
     __syncwarp();
     emit_part<EXTRA>(pj, cnt, base, row_global, o, sres, lane, jnext);
     return true;
@@ -816,15 +841,18 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_subbin_kernel(con
         }
         const float *px = a.part_x + row * a.row_stride + (i64)part * CAP;
         const u32 *pj = a.part_j + row * a.row_stride + (i64)part * CAP;
-        done = rank_part_subbin<EXTRA>(px, pj, a.X + row * a.ld, cnt, base, a.row0 + row, o, s_keys[wid], s_res[wid],
-                                       s_flag[wid], lane, 0.f, hi, have_range);
+        done = rank_part_subbin<16, EXTRA>(px, pj, a.X + row * a.ld, cnt, base, a.row0 + row, o, s_keys[wid],
+                                           s_res[wid], s_flag[wid], lane, 0.f, hi, have_range);
     }
     if (!done && lane == 0) a.biglist[atomicAdd(&a.bigcount[0], 1)] = make_int2((int)row, part);
 }
 
-// persistent: warps claim entries of the big-part work list
+// persistent: warps claim entries of the work list -- parts of 513..1024 values (sub-bin ranking with 128 bins
+// when `subbin`, the full sorting network otherwise or when a bin overflows) and the parts of at most 512 values
+// whose sub-bin ranking overflowed (sorting network).
 template <bool EXTRA>
-__global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const RankArgs a, const RankOut o) {
+__global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const RankArgs a, const RankOut o,
+                                                                          const int subbin) {
     __shared__ u32 s_keys[RANK_WARPS][CAP];
     __shared__ u32 s_res[RANK_WARPS][CAP];
     __shared__ u32 s_flag[RANK_WARPS][CAP];
@@ -836,7 +864,27 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const 
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= total) break;
         const int2 e = a.biglist[i];
-        rank_one<32, EXTRA>(a, o, (i64)e.x, e.y, a.cursor[(i64)e.x * a.P + e.y], s_keys[wid], s_res[wid], s_flag[wid], lane);
+        const i64 row = e.x;
+        const int part = e.y, cnt = a.cursor[row * a.P + part];
+        if (cnt <= CAP / 2) {
+            rank_one<16, EXTRA>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
+            continue;
+        }
+        bool done = false;
+        if (subbin) {
+            const int P = a.P;
+            const bool have_range = part > 0 && part < P - 1;
+            float hi = 0.f;
+            if (have_range) {
+                const float *sp = a.splitters_f + row * (P - 1);
+                hi = (float)((double)sp[part] - (double)sp[part - 1]);
+            }
+            done = rank_part_subbin<32, EXTRA>(a.part_x + row * a.row_stride + (i64)part * CAP,
+                                               a.part_j + row * a.row_stride + (i64)part * CAP, a.X + row * a.ld, cnt,
+                                               a.pbase[row * P + part], a.row0 + row, o, s_keys[wid], s_res[wid],
+                                               s_flag[wid], lane, 0.f, hi, have_range);
+        }
+        if (!done) rank_one<32, EXTRA>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
     }
 }
 
@@ -1287,11 +1335,11 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             if (o.acc3 || o.rank_b || o.group_rows) {
                 if (rank_subbin) mbd_rank_subbin_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
                 else mbd_rank_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
-                mbd_rank_big_kernel<true><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                mbd_rank_big_kernel<true><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o, rank_subbin);
             } else {
                 if (rank_subbin) mbd_rank_subbin_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
                 else mbd_rank_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
-                mbd_rank_big_kernel<false><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                mbd_rank_big_kernel<false><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o, rank_subbin);
             }
             SD_TRY(prof_end(ctx));
             ctx->last.launches += 3;

@@ -264,11 +264,59 @@ __global__ void __launch_bounds__(256) oja_kernel(const double *__restrict__ P, 
     if (threadIdx.x == 0) out[blockIdx.x] = tot / hull_volume;
 }
 
+// pool-relative inputs of the counting path: the pool's points, and each query's position inside the pool
+// (-1 if it is not a member; the reference only ever passes pool == queries, _pointcloud.py:182-193)
+__global__ void oja_gather_kernel(const double *__restrict__ P, const i64 *__restrict__ pool, const i64 npool,
+                                  const i64 *__restrict__ q, const i64 nq, double *__restrict__ pts,
+                                  i64 *__restrict__ qpos) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npool) {
+        const i64 s = pool ? pool[i] : i;
+        pts[2 * i] = P[2 * s];
+        pts[2 * i + 1] = P[2 * s + 1];
+    }
+    if (i < nq) {
+        const i64 want = q ? q[i] : i;
+        i64 pos = -1;
+        if (!pool) pos = want;
+        else if (i < npool && pool[i] == want) pos = i;
+        else
+            for (i64 k = 0; k < npool; ++k)
+                if (pool[k] == want) { pos = k; break; }
+        qpos[i] = pos;
+    }
+}
+
+__global__ void oja_check_members_kernel(const i64 *__restrict__ qpos, const i64 nq, int *__restrict__ flag) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq && qpos[i] < 0) atomicOr(flag, 1);
+}
+
+constexpr i64 OJA_ENUM_MAX_N = 256;
+
 int oja_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 nq, const i64 *d_pool, i64 npool,
                double hull_volume, double *d_out) {
     (void)n;
     if (nq == 0) return SD_OK;
     cudaStream_t st = ctx->stream;
+    if (d == 2 && (ctx->simplicial_impl == SD_SIMPLICIAL_COUNT ||
+                   (ctx->simplicial_impl == SD_SIMPLICIAL_AUTO && npool > OJA_ENUM_MAX_N))) {
+        // O(n log n) per query; queries that are not pool members keep the enumeration (never the case for
+        // the reference's call pattern)
+        SD_TRY(ctx->buf[BUF_MISC].reserve((size_t)npool * 2 * sizeof(double) + (size_t)nq * sizeof(i64) + 64));  // BUF_AUX holds the pool
+        double *pts = ctx->buf[BUF_MISC].as<double>();
+        i64 *qpos = reinterpret_cast<i64 *>(pts + 2 * npool);
+        int *flag = ctx->d_status + 4;  // [0..3] belong to the status word and the rank pipeline
+        SD_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+        const i64 m = npool > nq ? npool : nq;
+        oja_gather_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(dP, d_pool, npool, d_q, nq, pts, qpos);
+        oja_check_members_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(qpos, nq, flag);
+        ctx->last.launches += 2;
+        int h_flag = 0;
+        SD_CUDA(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaStreamSynchronize(st));
+        if (!h_flag) return oja2_count_device(ctx, pts, npool, qpos, nq, hull_volume, d_out);
+    }
     if (d == 2) oja_kernel<2><<<(unsigned)nq, 256, 0, st>>>(dP, d_q, d_pool, npool, hull_volume, d_out);
     else if (d == 3) oja_kernel<3><<<(unsigned)nq, 256, 0, st>>>(dP, d_q, d_pool, npool, hull_volume, d_out);
     else { set_error("oja: d=%d not supported", d); return SD_ERR_UNSUPPORTED; }

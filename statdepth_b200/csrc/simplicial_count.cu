@@ -34,52 +34,10 @@
 // the open half-turns of the exact formula.  Angles here come from atan2 / acos (a few ulp): decisions can
 // differ from the enumeration predicate only for triangles whose distance to p is within ~1e-15 |x - p| of
 // tol, far inside the documented tie band of the LP itself (DESIGN.md "Oracle and parity").
+#include "angular_key.cuh"
 #include "common.cuh"
 
 namespace sd {
-
-constexpr double SC_ZERO = 8.0 + 9.0;   // direction is the zero vector (point coincides with the query)
-constexpr double SC_SELF = 8.0 + 10.0;  // the query's own entry
-
-// instance -> (query index, offset of its coordinates); mode 0: point cloud, mode 1: functional (q, t)
-struct ScGeom {
-    const double *pts;   // point j of instance i at pts[j * stride_j + inst_off(i) + {0,1}]
-    i64 stride_j;
-    const i64 *qidx;     // query ids (may be null = identity)
-    i64 T;               // functional: instances per query (time points); point cloud: 1
-    i64 inst0;           // first instance of this batch
-};
-
-__device__ __forceinline__ i64 sc_query(const ScGeom &g, i64 inst) {
-    const i64 qi = inst / g.T;
-    return g.qidx ? g.qidx[qi] : qi;
-}
-__device__ __forceinline__ i64 sc_off(const ScGeom &g, i64 inst) { return (inst % g.T) * 2; }
-
-// exact-monotone angular key of a non-zero direction, in [8, 16)
-__device__ __forceinline__ double sc_key(double dx, double dy) {
-    double add = 8.0;
-    if (dy < 0.0 || (dy == 0.0 && dx < 0.0)) {  // lower half-plane (and the negative x axis): rotate by pi
-        dx = -dx;
-        dy = -dy;
-        add = 12.0;
-    }
-    // now dy > 0, or dy == 0 and dx > 0: angle in [0, pi)
-    double oct, f;
-    if (dx > 0.0) {
-        if (dy < dx) { oct = 0.0; f = dy / dx; }            // [0, pi/4)
-        else         { oct = 1.0; f = 1.0 - dx / dy; }      // [pi/4, pi/2)
-    } else {
-        const double ax = -dx;
-        if (ax < dy) { oct = 2.0; f = ax / dy; }            // [pi/2, 3pi/4)
-        else         { oct = 3.0; f = 1.0 - dy / ax; }      // [3pi/4, pi)
-    }
-    // f in [0,1): one rounding to the [8,16) binade, monotone.  A direction a hair below the +x axis
-    // (f = 1 - tiny rounds to 1, or 15 + f rounds up) would land on 16.0, the value range of the sentinels:
-    // angle 2 pi IS angle 0, so it folds back onto 8.0 (its antipode is then exactly 12.0).
-    const double k = (add + oct) + f;
-    return k >= 16.0 ? 8.0 : k;
-}
 
 constexpr double SC_TWO_PI = 6.283185307179586476925286766559;
 
@@ -257,6 +215,171 @@ int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride
         SD_TRY(mbd_all_device(ctx, KB, ni, 2 * n, 2 * n, false, nullptr, nullptr, bB, tol > 0.0 ? aB : nullptr));
         if (tol > 0.0) sc_reduce_kernel<true><<<(unsigned)ni, 256, 0, st>>>(g, n, KA, KB, bA, aA, bB, aB, claim, d_out);
         else sc_reduce_kernel<false><<<(unsigned)ni, 256, 0, st>>>(g, n, KA, KB, bA, aA, bB, aB, claim, d_out);
+        ctx->last.launches++;
+        SD_CUDA(cudaGetLastError());
+    }
+    return SD_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Oja depth, d = 2, in O(n log n) per query.  Replaces the enumeration of all pairs in _oja_depth
+// (statdepth/depth/calculations/_pointcloud.py:176-204):  sum over pairs {a, b} of the pool of
+// area(p, x_a, x_b) = |det(v_a, v_b)| / 2, v = x - p.  With the directions sorted by angle, every pair is
+// counted once as (a, b) with b strictly inside the half-turn counter-clockwise of a, where det(v_a, v_b) > 0
+// (pairs on one line through p have area 0), and det is linear in its second argument:
+//     sum = 1/2 sum_a det(v_a, S_a),   S_a = sum of v_b over that half-turn
+//         = prefix sums W[r] = sum of v_b with rank < r, taken at the rank of a's class end and of its antipode.
+// Ranks come from the same two passes of the K1 pipeline as the triangle counting (exact keys, tolerance 0).
+// One CTA per query: bucket sums by rank (float64 atomics; only tied directions share a bucket), a block-wide
+// exclusive scan, one pass over the points.  The summation order differs from the reference's pair loop:
+// agreement is to ~1e-14 relative at n = 200 (tests: 1e-12).
+// ---------------------------------------------------------------------------------------------
+constexpr int OJ_THREADS = 512;
+
+__global__ void __launch_bounds__(OJ_THREADS) oja2_reduce_kernel(const ScGeom g, const i64 n, const double *__restrict__ KA,
+                                                                 const int *__restrict__ bA, const int *__restrict__ aA,
+                                                                 const int *__restrict__ bB, double *__restrict__ bucket,
+                                                                 const double hull_volume, double *__restrict__ out) {
+    __shared__ double s_part[2][OJ_THREADS];
+    __shared__ double s_red[OJ_THREADS / 32];
+    __shared__ i64 s_cnt[2];
+    __shared__ double s_tot[2];
+    const i64 li = blockIdx.x;
+    const i64 inst = g.inst0 + li;
+    const i64 q = sc_query(g, inst);
+    const double px = g.pts[q * g.stride_j], py = g.pts[q * g.stride_j + 1];
+    const double *ka = KA + li * n;
+    const int *ba = bA + li * n, *aa = aA + li * n, *bb = bB + li * 2 * n;
+    double *bx = bucket + li * 2 * (n + 1), *by = bx + (n + 1);
+    const int tid = threadIdx.x;
+    for (i64 r = tid; r < 2 * (n + 1); r += OJ_THREADS) bx[r] = 0.0;
+    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_tot[0] = 0.0; s_tot[1] = 0.0; }
+    __syncthreads();
+    // pass 1: bucket sums by rank, totals, #real directions and #directions in [0, pi)
+    i64 real = 0, low = 0;
+    double tx = 0.0, ty = 0.0;
+    for (i64 j = tid; j < n; j += OJ_THREADS) {
+        const double u = ka[j];
+        if (!(u < 16.0)) continue;
+        const double vx = g.pts[j * g.stride_j] - px, vy = g.pts[j * g.stride_j + 1] - py;
+        atomicAdd(&bx[ba[j]], vx);
+        atomicAdd(&by[ba[j]], vy);
+        tx += vx;
+        ty += vy;
+        ++real;
+        low += u < 12.0;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        real += __shfl_xor_sync(0xffffffffu, real, s);
+        low += __shfl_xor_sync(0xffffffffu, low, s);
+        tx += __shfl_xor_sync(0xffffffffu, tx, s);
+        ty += __shfl_xor_sync(0xffffffffu, ty, s);
+    }
+    if ((tid & 31) == 0) {
+        atomicAdd((u64 *)&s_cnt[0], (u64)real);
+        atomicAdd((u64 *)&s_cnt[1], (u64)low);
+        atomicAdd(&s_tot[0], tx);
+        atomicAdd(&s_tot[1], ty);
+    }
+    __syncthreads();
+    // pass 2: exclusive scan of the buckets in place: W[r] = sum of v_b with rank < r   (r = 0 .. n)
+    const i64 len = n + 1, chunk = (len + OJ_THREADS - 1) / OJ_THREADS;
+    const i64 c0 = tid * chunk, c1 = c0 + chunk < len ? c0 + chunk : len;
+    double sx = 0.0, sy = 0.0;
+    for (i64 r = c0; r < c1; ++r) { sx += bx[r]; sy += by[r]; }
+    s_part[0][tid] = sx;
+    s_part[1][tid] = sy;
+    __syncthreads();
+    if (tid < 2) {  // 512 partial sums per coordinate: a serial scan by one thread each is negligible
+        double run = 0.0;
+        for (int k = 0; k < OJ_THREADS; ++k) { const double v = s_part[tid][k]; s_part[tid][k] = run; run += v; }
+    }
+    __syncthreads();
+    sx = s_part[0][tid];
+    sy = s_part[1][tid];
+    for (i64 r = c0; r < c1; ++r) {
+        const double vx = bx[r], vy = by[r];
+        bx[r] = sx;
+        by[r] = sy;
+        sx += vx;
+        sy += vy;
+    }
+    __syncthreads();
+    // pass 3
+    const i64 mreal = s_cnt[0], L4 = s_cnt[1], H = mreal - L4;
+    const double totx = s_tot[0], toty = s_tot[1];
+    double acc = 0.0;
+    for (i64 j = tid; j < n; j += OJ_THREADS) {
+        const double u = ka[j];
+        if (!(u < 16.0)) continue;
+        const double vx = g.pts[j * g.stride_j] - px, vy = g.pts[j * g.stride_j + 1] - py;
+        const i64 L = ba[j], R = n - (i64)aa[j];  // ranks [L, R) hold the class of j
+        const i64 b2w = bb[n + j];
+        double hx, hy;
+        if (u < 12.0) {
+            const i64 Lw = b2w - L - H;           // real directions strictly before the antipode
+            hx = bx[Lw] - bx[R];
+            hy = by[Lw] - by[R];
+        } else {
+            const i64 Lw = b2w - L + L4;
+            hx = (totx - bx[R]) + bx[Lw];
+            hy = (toty - by[R]) + by[Lw];
+        }
+        acc += vx * hy - vy * hx;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if ((tid & 31) == 0) s_red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < OJ_THREADS / 32; ++w) tot += s_red[w];
+        out[inst] = 0.5 * tot / hull_volume;
+    }
+}
+
+// d_pts: the pool's points [n][2] (already gathered); d_q: positions of the queries inside the pool
+int oja2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, const i64 *d_q, i64 nq, double hull_volume,
+                      double *d_out) {
+    cudaStream_t st = ctx->stream;
+    if (nq == 0) return SD_OK;
+    if (n < 3) {  // no pair of other points
+        SD_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nq * sizeof(double), st));
+        return SD_OK;
+    }
+    if (2 * n >= (1ll << 31)) {
+        set_error("oja counting: n=%lld too large", (long long)n);
+        return SD_ERR_UNSUPPORTED;
+    }
+    i64 IB = (i64)((3ull << 30) / (size_t)(72 * n));
+    if (IB < 1) IB = 1;
+    if (IB > 32768) IB = 32768;
+    if (IB > nq) IB = nq;
+    SD_TRY(ctx->buf[BUF_IN2].reserve((size_t)IB * (3 * n + 2 * (n + 1)) * sizeof(double)));
+    SD_TRY(ctx->buf[BUF_MASK].reserve((size_t)IB * n * 4 * sizeof(int)));
+    double *KA = ctx->buf[BUF_IN2].as<double>();
+    double *KB = KA + (size_t)IB * n;
+    double *bucket = KB + (size_t)IB * 2 * n;
+    int *bA = ctx->buf[BUF_MASK].as<int>();
+    int *aA = bA + (size_t)IB * n;
+    int *bB = aA + (size_t)IB * n;
+    ScGeom g;
+    g.pts = d_pts;
+    g.stride_j = 2;
+    g.qidx = d_q;
+    g.T = 1;
+    for (i64 i0 = 0; i0 < nq; i0 += IB) {
+        const i64 ni = nq - i0 < IB ? nq - i0 : IB;
+        g.inst0 = i0;
+        unsigned gx = (unsigned)ceil_div(n, 256 * 4);
+        if (gx < 1) gx = 1;
+        sc_keys_kernel<<<dim3(gx, (unsigned)ni), 256, 0, st>>>(g, n, ni, 0.0, KA, KB, ctx->d_status);
+        ctx->last.launches++;
+        SD_TRY(mbd_all_device(ctx, KA, ni, n, n, false, nullptr, nullptr, bA, aA));
+        SD_TRY(mbd_all_device(ctx, KB, ni, 2 * n, 2 * n, false, nullptr, nullptr, bB, nullptr));
+        oja2_reduce_kernel<<<(unsigned)ni, OJ_THREADS, 0, st>>>(g, n, KA, bA, aA, bB, bucket, hull_volume, d_out);
         ctx->last.launches++;
         SD_CUDA(cudaGetLastError());
     }

@@ -245,23 +245,14 @@ def permutation_test(F: pd.DataFrame, G: pd.DataFrame, method='p1', B=200, seed=
         return np.array([stat(pooled.iloc[:, perms[b][:nF]], pooled.iloc[:, perms[b][nF:]]) for b in block])
 
     # the inner depth calls must not shard again while permutations are sharded across ranks
-    import os
-    prev = os.environ.get("STATDEPTH_DISTRIBUTED")
     rank, size = _dist.world()
-    try:
-        if size > 1:
-            lo, hi = _dist.block(B, rank, size)
-            os.environ["STATDEPTH_DISTRIBUTED"] = "0"
+    if size > 1:
+        lo, hi = _dist.block(B, rank, size)
+        with _dist.local_only():
             local = run(range(lo, hi))
-            os.environ["STATDEPTH_DISTRIBUTED"] = "1" if prev is None else prev
-            null = _dist.allgather_blocks(local.astype(np.float64), B)
-        else:
-            null = run(range(B))
-    finally:
-        if prev is None:
-            os.environ.pop("STATDEPTH_DISTRIBUTED", None)
-        else:
-            os.environ["STATDEPTH_DISTRIBUTED"] = prev
+        null = _dist.allgather_blocks(local.astype(np.float64), B)
+    else:
+        null = run(range(B))
     if method == 'p2':   # p2: small = homogeneous
         p = float((np.sum(null >= observed) + 1) / (B + 1))
     else:                # p1 / p3: large = homogeneous

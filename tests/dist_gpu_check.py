@@ -14,7 +14,7 @@ import torch.distributed as dist
 rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-from statdepth_b200 import FunctionalDepth, PointcloudDepth  # noqa: E402
+from statdepth_b200 import FunctionalDepth, PointcloudDepth, enable_distributed  # noqa: E402
 from statdepth_b200.homogeneity import permutation_test  # noqa: E402
 
 rng = np.random.default_rng(3)
@@ -30,8 +30,9 @@ def run():
                 perm=permutation_test(F, G, B=11, seed=1)["null"])
 
 
+enable_distributed(True)
 multi = run()
-os.environ["STATDEPTH_DISTRIBUTED"] = "0"
+enable_distributed(False)
 single = run()
 ok = all(np.array_equal(multi[k], single[k]) for k in multi)
 print("rank", rank, "OK" if ok else "MISMATCH", {k: float(np.abs(multi[k] - single[k]).max()) for k in multi}, flush=True)

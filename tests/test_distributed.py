@@ -27,11 +27,13 @@ def _worker(rank, world, port, out_dir):
     from conftest import OracleBackedEngine
     import statdepth_b200._functional as f
     import statdepth_b200._pointcloud as p
-    from statdepth_b200 import FunctionalDepth, PointcloudDepth, _dist
+    from statdepth_b200 import FunctionalDepth, PointcloudDepth, _dist, enable_distributed
     fake = OracleBackedEngine()
     f.get_engine = lambda device=None: fake
     p.get_engine = lambda device=None: fake
 
+    assert _dist.world() == (0, 1)  # an initialised process group alone does not shard: opt-in
+    enable_distributed()
     assert _dist.world() == (rank, world)
     rng = np.random.default_rng(9)
     X = rng.standard_normal((13, 17)).cumsum(0)  # 13 rows: uneven split 7 + 6

@@ -670,6 +670,30 @@ def test_oja(engine, oracle, n, d, seed):
     np.testing.assert_allclose(engine.oja(P, hv, pool, pool), oracle.oja(P, hv, pool, pool), rtol=RTOL)
 
 
+def test_oja_angular_sums(engine, oracle):
+    """Oja depth in 2-D by angular prefix sums (O(n log n) per query; AUTO above 256 points) against the
+    oracle's pair enumeration: general position, a lattice (collinear pairs have area 0), a pool, and the size
+    at which AUTO switches.  Different summation order: 1e-12 relative, as for every float64 result."""
+    from scipy.spatial import ConvexHull
+    from statdepth_b200 import _engine as E
+    rng = np.random.default_rng(23)
+    try:
+        engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_COUNT)
+        for n, lattice in ((3, False), (4, False), (37, False), (60, True), (300, False)):
+            P = rng.integers(0, 6, size=(n, 2)).astype(np.float64) if lattice else rng.standard_normal((n, 2))
+            hv = ConvexHull(P).volume if n > 3 else 1.0
+            np.testing.assert_allclose(engine.oja(P, hv), oracle.oja(P, hv), rtol=RTOL, atol=1e-13)
+        P = rng.standard_normal((80, 2))
+        pool = np.array([5, 0, 33, 79, 12, 40, 41, 7])
+        np.testing.assert_allclose(engine.oja(P, 2.5, pool, pool), oracle.oja(P, 2.5, pool, pool), rtol=RTOL)
+        np.testing.assert_allclose(engine.oja(P, 2.5, [3, 5], pool), oracle.oja(P, 2.5, [3, 5], pool), rtol=RTOL)
+    finally:
+        engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_AUTO)
+    P = rng.standard_normal((1200, 2))  # AUTO: counted; 50 queries against the enumeration
+    q = rng.choice(1200, 50, replace=False)
+    np.testing.assert_allclose(engine.oja(P, 7.0, q), oracle.oja(P, 7.0, q), rtol=RTOL)
+
+
 @pytest.mark.parametrize("N,T,d,seed", [(12, 9, 2, 0), (9, 5, 3, 1), (10, 7, 1, 2), (30, 16, 2, 3)])
 def test_simplex_depth_counts(engine, oracle, N, T, d, seed):
     F = np.random.default_rng(seed).standard_normal((N, T, d)).cumsum(1)
