@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
 #ifndef SD_PT_EPT
 #define SD_PT_EPT 16
 #endif
+#ifndef SD_PT_MINB
+#define SD_PT_MINB (SD_PT_THREADS >= 512 ? 2 : 3)  // resident CTAs per SM the register budget is held to
+#endif
 constexpr int PT_THREADS = SD_PT_THREADS;
 constexpr int PT_EPT = SD_PT_EPT;               // values per thread
 constexpr int PT_CHUNK = PT_THREADS * PT_EPT;   // 4096 values per CTA
@@ -246,7 +249,7 @@ __device__ __forceinline__ int part_of(const float f, const float *__restrict__ 
     return idx;
 }
 
-__global__ void __launch_bounds__(PT_THREADS, PT_THREADS >= 512 ? 2 : 3) mbd_partition_kernel(const double *__restrict__ X, i64 n, i64 ld, int P,
+__global__ void __launch_bounds__(PT_THREADS, SD_PT_MINB) mbd_partition_kernel(const double *__restrict__ X, i64 n, i64 ld, int P,
                                                                    const float *__restrict__ splitters_f,
                                                                    const unsigned short *__restrict__ tables,
                                                                    int *__restrict__ cursor, int *__restrict__ rowflag,

@@ -303,8 +303,8 @@ int oja_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 
                    (ctx->simplicial_impl == SD_SIMPLICIAL_AUTO && npool > OJA_ENUM_MAX_N))) {
         // O(n log n) per query; queries that are not pool members keep the enumeration (never the case for
         // the reference's call pattern)
-        SD_TRY(ctx->buf[BUF_MISC].reserve((size_t)npool * 2 * sizeof(double) + (size_t)nq * sizeof(i64) + 64));  // BUF_AUX holds the pool
-        double *pts = ctx->buf[BUF_MISC].as<double>();
+        SD_TRY(ctx->buf[BUF_GEOM].reserve((size_t)npool * 2 * sizeof(double) + (size_t)nq * sizeof(i64) + 64));
+        double *pts = ctx->buf[BUF_GEOM].as<double>();
         i64 *qpos = reinterpret_cast<i64 *>(pts + 2 * npool);
         int *flag = ctx->d_status + 4;  // [0..3] belong to the status word and the rank pipeline
         SD_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
