@@ -189,6 +189,17 @@ int sd_pointcloud_oja_f64(sd_ctx *ctx, const double *P, int64_t n, int d, const 
                           double *out);
 
 /*
+ * B small sub-clouds of one cloud with ONE query each, in one launch: what K-sampled point-cloud depth consists
+ * of (_samplepointwisedepth, _pointcloud.py:97-123).  Block b holds the points member[block_off[b] .. block_off[b+1])
+ * (ids into P, in the reference's order: the L1 sum runs in that order, bit for bit), its query is the member at
+ * position query_pos[b].  kind 0: simplicial count (returned as a double, exact below 2^53), 1: L1 depth,
+ * 2: Oja sum / hull_volume[b] (d in {2,3}).  At most 4096 / d members per block (they are enumerated).
+ */
+int sd_pointcloud_blocks_f64(sd_ctx *ctx, const double *P, int64_t n, int d, const int64_t *member,
+                             const int64_t *block_off, const int64_t *query_pos, int64_t B, int kind, double tol,
+                             const double *hull_volume, double *out);
+
+/*
  * Batched band depth over sub-populations of one matrix (K-sampled blocks, homogeneity
  * permutations): membership[b*n + c] != 0 selects the curves of batch b; queries[b*nqb + i] is
  * the i-th query curve of batch b (must be a member).  count_out[b*nqb + i] as in

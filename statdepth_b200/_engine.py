@@ -74,6 +74,8 @@ SIGNATURES = {
                                        C.c_void_p]),
     "sd_pointcloud_oja_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
+    "sd_pointcloud_blocks_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "sd_band_depth_batched_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                             C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
 }
@@ -286,6 +288,25 @@ class Engine:
         out = np.empty(nq, dtype=np.float64)
         self._check(self.lib.sd_pointcloud_oja_f64(self._ctx, _ptr(P), n, d, _ptr(q), nq, _ptr(pl), npool,
                                                    float(hull_volume), _ptr(out)))
+        return out
+
+
+    BLOCK_KINDS = {"simplex": 0, "l1": 1, "oja": 2}
+
+    def cloud_blocks(self, P, members, offsets, query_pos, kind, tol=1e-7, hull_volumes=None):
+        """One single-query depth per block of member points (K-sampled point-cloud depth), one launch for all.
+        members: concatenated point ids; offsets [B+1]; query_pos [B] position of the query inside its block.
+        Returns float64 [B]: simplicial COUNT (exact), L1 depth, or Oja sum / hull_volumes[b]."""
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        n, d = P.shape
+        mem = np.ascontiguousarray(members, dtype=np.int64)
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        qp = np.ascontiguousarray(query_pos, dtype=np.int64)
+        B = int(qp.size)
+        hv = None if hull_volumes is None else np.ascontiguousarray(hull_volumes, dtype=np.float64)
+        out = np.empty(B, dtype=np.float64)
+        self._check(self.lib.sd_pointcloud_blocks_f64(self._ctx, _ptr(P), n, d, _ptr(mem), _ptr(off), _ptr(qp), B,
+                                                      int(self.BLOCK_KINDS[kind]), float(tol), _ptr(hv), _ptr(out)))
         return out
 
 

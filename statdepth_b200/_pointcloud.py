@@ -100,22 +100,51 @@ def _samplepointwisedepth(
     containment='simplex',
     quiet=True,
 ) -> pd.Series:
-    """Sampled point-cloud depth; mirrors _pointcloud.py:68-123 including its quirk that the inner
-    loop runs ss = n // K times (not K) with blocks of ss rows drawn by `DataFrame.sample` from the
-    global numpy RNG (same call sequence -> same stream as the reference)."""
+    """Sampled point-cloud depth; mirrors _pointcloud.py:68-123 including its quirk that the inner loop runs
+    ss = n // K times (not K) with blocks of ss rows drawn by `DataFrame.sample` from the global numpy RNG
+    (same call sequence -> same stream as the reference).  The len(to_compute) * ss single-query blocks are
+    evaluated by ONE engine call (sd_pointcloud_blocks_f64) for 'simplex' and 'l1'."""
     if K == 1:
         return _pointwisedepth(data=data, to_compute=to_compute, containment=containment)
     n, d = data.shape
-    depths = []
     if to_compute is None:
         to_compute = data.index
     ss = n // K
+    if containment not in ('simplex', 'l1') or d > 3 or (ss + 1) * d > 4096 or ss == 0:
+        # 'oja' with to_compute=[point] enumerates subsets of that one point (reference quirk, :182-193) and
+        # 'mahalanobis' is a host routine: both keep the reference's loop of single calls
+        depths = []
+        for time in to_compute:
+            cd = []
+            for _ in range(ss):
+                sdata = data.sample(n=ss, axis=0)
+                if time not in sdata.index:
+                    sdata = pd.concat([sdata, data.loc[[time], :]])
+                cd.append(_pointwisedepth(data=sdata, to_compute=[time], containment=containment))
+            depths.append(np.mean(cd))
+        return pd.Series(index=to_compute, data=depths)
+
+    # label-level replay of the sampling (same pandas calls on a one-column frame with the same index)
+    labels = pd.DataFrame(np.zeros((n, 1)), index=data.index)
+    members, offsets, qpos = [], [0], []
     for time in to_compute:
-        cd = []
+        tpos = int(_positions([time], data.index, 'to_compute')[0])
         for _ in range(ss):
-            sdata = data.sample(n=ss, axis=0)
-            if time not in sdata.index:
-                sdata = pd.concat([sdata, data.loc[[time], :]])
-            cd.append(_pointwisedepth(data=sdata, to_compute=[time], containment=containment))
-        depths.append(np.mean(cd))
+            pos = _positions(labels.sample(n=ss, axis=0).index, data.index, 'sampled rows')
+            hit = np.flatnonzero(pos == tpos)
+            if hit.size:
+                qpos.append(int(hit[0]))
+            else:  # the reference appends the point at the END of the sampled frame (:118)
+                pos = np.append(pos, tpos)
+                qpos.append(len(pos) - 1)
+            members.append(pos)
+            offsets.append(offsets[-1] + len(pos))
+    P = np.ascontiguousarray(_values(data))
+    eng = get_engine()
+    sizes = np.diff(np.asarray(offsets, dtype=np.int64)).astype(np.float64)
+    vals = eng.cloud_blocks(P, np.concatenate(members) if members else np.zeros(0, np.int64), offsets, qpos,
+                            containment, settings.get_simplex_tolerance())
+    if containment == 'simplex':
+        vals = vals / binom(sizes, d + 1)  # _pointcloud.py:56 with n = len(sdata)
+    depths = [np.mean(vals[i * ss:(i + 1) * ss]) for i in range(len(to_compute))]
     return pd.Series(index=to_compute, data=depths)

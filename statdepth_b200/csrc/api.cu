@@ -1,5 +1,6 @@
 // api.cu -- extern "C" entry points taking HOST buffers (copies + kernels + copy back), and the
 // device-pointer variant used for HBM-resident timing.  See include/statdepth_b200.h.
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -75,6 +76,8 @@ int band_depth_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const
     SD_TRY(ctx->buf[BUF_ACC].reserve((size_t)n * 2 * sizeof(i64)));
     i64 *acc2 = ctx->buf[BUF_ACC].as<i64>();
     i64 *acc3 = acc2 + n;
+    if (!d_q && j == 2)  // all curves, in order: the finish kernel writes the caller's buffer, no gather launch
+        return mbd_all_device(ctx, dX, T, n, ld, false, d_out, nullptr, nullptr, nullptr);
     SD_TRY(mbd_all_device(ctx, dX, T, n, ld, j == 3, acc2, acc3, nullptr, nullptr));
     return gather_i64_device(ctx, j == 2 ? acc2 : acc3, d_q, nq, d_out);
 }
@@ -129,6 +132,35 @@ static int upload_queries(sd_ctx *ctx, const int64_t *h_q, i64 nq, i64 n, const 
     return SD_OK;
 }
 
+// Pageable host input (what FunctionalDepth([DataFrame]) hands over): cudaMemcpyAsync from unregistered memory is a
+// synchronous, single-threaded staged copy (~11 GB/s measured: 74 ms for the 819 MB of config 2 against 15 ms from
+// pinned memory).  The blocks are instead copied into two pinned staging buffers by a few host threads while the
+// previous block's DMA and ranking run.
+static bool host_is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static void parallel_copy_rows(double *dst, const double *src, i64 rows, i64 n, i64 ld, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> th;
+    const i64 per = ceil_div(rows, nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        const i64 r0 = t * per, r1 = r0 + per < rows ? r0 + per : rows;
+        if (r0 >= r1) break;
+        th.emplace_back([=]() {
+            if (ld == n) memcpy(dst + r0 * n, src + r0 * ld, (size_t)(r1 - r0) * n * sizeof(double));
+            else
+                for (i64 r = r0; r < r1; ++r) memcpy(dst + r * n, src + r * ld, (size_t)n * sizeof(double));
+        });
+    }
+    for (auto &t : th) t.join();
+}
+
 // Relaxed band depth of a host matrix, streamed in row blocks (see sd_band_depth_f64).  Timings: h2d_ns is 0
 // and kernel_ns covers the overlapped copy + ranking region.
 static int band_depth_pipelined(sd_ctx *ctx, const double *X, i64 T, i64 n, i64 ld, const int64_t *query_idx, i64 nq,
@@ -157,23 +189,53 @@ static int band_depth_pipelined(sd_ctx *ctx, const double *X, i64 T, i64 n, i64 
     // the copy stream must not overtake work already queued on the main stream (query upload, status reset)
     SD_CUDA(cudaEventRecord(ctx->ev_pipe[2], ctx->stream));
     SD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[2], 0));
-    int k = 0;
-    for (i64 r0 = 0; r0 < T; r0 += RB, ++k) {
-        const int s = k & 1;
-        const i64 rows = T - r0 < RB ? T - r0 : RB;
-        if (k >= 2) SD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[2 + s], 0));  // block k-2 consumed
-        if (ld == n) {
-            SD_CUDA(cudaMemcpyAsync(dbuf[s], X + r0 * ld, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice,
-                                    ctx->copy_stream));
-        } else {
-            SD_CUDA(cudaMemcpy2DAsync(dbuf[s], (size_t)n * sizeof(double), X + r0 * ld, (size_t)ld * sizeof(double),
-                                      (size_t)n * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice,
-                                      ctx->copy_stream));
+    const bool staged = host_is_pageable(X);
+    int nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads > 8) nthreads = 8;
+    if (staged) {
+        for (int s = 0; s < 2; ++s) {
+            if (ctx->stage_cap[s] < (size_t)RB * n * sizeof(double)) {
+                if (ctx->stage[s]) cudaFreeHost(ctx->stage[s]);
+                ctx->stage[s] = nullptr;
+                ctx->stage_cap[s] = 0;
+                SD_CUDA(cudaHostAlloc(&ctx->stage[s], (size_t)RB * n * sizeof(double), cudaHostAllocDefault));
+                ctx->stage_cap[s] = (size_t)RB * n * sizeof(double);
+            }
+            if (!ctx->ev_stage[s]) SD_CUDA(cudaEventCreateWithFlags(&ctx->ev_stage[s], cudaEventDisableTiming));
         }
-        SD_CUDA(cudaEventRecord(ctx->ev_pipe[s], ctx->copy_stream));
-        SD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[s], 0));
-        SD_TRY(mbd_all_device(ctx, dbuf[s], rows, n, n, j == 3, acc2, acc3, nullptr, nullptr, k > 0));
-        SD_CUDA(cudaEventRecord(ctx->ev_pipe[2 + s], ctx->stream));
+    }
+    // an error inside the loop must not return while a copy out of the caller's buffer is still in flight
+    const int loop_status = [&]() -> int {
+        int k = 0;
+        for (i64 r0 = 0; r0 < T; r0 += RB, ++k) {
+            const int s = k & 1;
+            const i64 rows = T - r0 < RB ? T - r0 : RB;
+            if (k >= 2) SD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[2 + s], 0));  // block k-2 consumed
+            if (staged) {
+                if (k >= 2) SD_CUDA(cudaEventSynchronize(ctx->ev_stage[s]));  // the DMA out of this staging buffer is done
+                parallel_copy_rows((double *)ctx->stage[s], X + r0 * ld, rows, n, ld, nthreads);
+                SD_CUDA(cudaMemcpyAsync(dbuf[s], ctx->stage[s], (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice,
+                                        ctx->copy_stream));
+                SD_CUDA(cudaEventRecord(ctx->ev_stage[s], ctx->copy_stream));
+            } else if (ld == n) {
+                SD_CUDA(cudaMemcpyAsync(dbuf[s], X + r0 * ld, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice,
+                                        ctx->copy_stream));
+            } else {
+                SD_CUDA(cudaMemcpy2DAsync(dbuf[s], (size_t)n * sizeof(double), X + r0 * ld, (size_t)ld * sizeof(double),
+                                          (size_t)n * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice,
+                                          ctx->copy_stream));
+            }
+            SD_CUDA(cudaEventRecord(ctx->ev_pipe[s], ctx->copy_stream));
+            SD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[s], 0));
+            SD_TRY(mbd_all_device(ctx, dbuf[s], rows, n, n, j == 3, acc2, acc3, nullptr, nullptr, k > 0));
+            SD_CUDA(cudaEventRecord(ctx->ev_pipe[2 + s], ctx->stream));
+        }
+        return SD_OK;
+    }();
+    if (loop_status != SD_OK) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        return loop_status;
     }
     SD_TRY(gather_i64_device(ctx, j == 2 ? acc2 : acc3, d_q, nq, d_out));
     SD_TRY(mark(ctx, 2));
@@ -476,6 +538,50 @@ int sd_band_depth_f64_dev(sd_ctx *ctx, const double *dX, int64_t T, int64_t n, i
         sd::set_error("sd_band_depth_f64_dev: out of host memory");
         return SD_ERR_INVALID;
     }
+}
+
+int sd_pointcloud_blocks_f64(sd_ctx *ctx, const double *P, int64_t n, int d, const int64_t *member,
+                             const int64_t *block_off, const int64_t *query_pos, int64_t B, int kind, double tol,
+                             const double *hull_volume, double *out) {
+    SD_TRY(check_common(ctx, P, out, "sd_pointcloud_blocks_f64"));
+    SD_REQUIRE(n >= 1 && B >= 0 && member && block_off && query_pos, "sd_pointcloud_blocks_f64: bad arguments");
+    SD_REQUIRE(d >= 1 && d <= 3, "sd_pointcloud_blocks_f64: d=%d not supported (1..3)", d);
+    SD_REQUIRE(kind >= 0 && kind <= 2, "sd_pointcloud_blocks_f64: kind=%d (0 simplicial, 1 l1, 2 oja)", kind);
+    SD_REQUIRE(kind != 2 || (hull_volume && d >= 2), "sd_pointcloud_blocks_f64: oja needs d in (2, 3) and hull volumes");
+    SD_REQUIRE(tol >= 0.0, "sd_pointcloud_blocks_f64: tol must be >= 0");
+    SD_REQUIRE(block_off[0] == 0, "sd_pointcloud_blocks_f64: block_off[0] must be 0");
+    for (i64 b = 0; b < B; ++b) {
+        const i64 m = block_off[b + 1] - block_off[b];
+        SD_REQUIRE(m >= 1 && m * d <= 4096, "sd_pointcloud_blocks_f64: block %lld has %lld members (1 .. %d supported)",
+                   (long long)b, (long long)m, 4096 / d);
+        SD_REQUIRE(query_pos[b] >= 0 && query_pos[b] < m, "sd_pointcloud_blocks_f64: query_pos[%lld] out of range",
+                   (long long)b);
+    }
+    const i64 total = B > 0 ? block_off[B] : 0;
+    for (i64 i = 0; i < total; ++i)
+        SD_REQUIRE(member[i] >= 0 && member[i] < n, "sd_pointcloud_blocks_f64: member[%lld] out of range", (long long)i);
+    SD_TRY(begin_call(ctx));
+    double *dP = nullptr;
+    SD_TRY(upload_matrix(ctx, BUF_IN, P, 1, n * d, n * d, &dP));
+    // member | block_off | query_pos | hull volumes | out, in one workspace buffer
+    const size_t words = (size_t)total + (size_t)(B + 1) + (size_t)B + (size_t)B + (size_t)B + 8;
+    SD_TRY(ctx->buf[BUF_AUX].reserve(words * 8));
+    i64 *d_member = ctx->buf[BUF_AUX].as<i64>();
+    i64 *d_off = d_member + total;
+    i64 *d_qpos = d_off + (B + 1);
+    double *d_vol = reinterpret_cast<double *>(d_qpos + B);
+    double *d_out = d_vol + B;
+    if (total > 0) SD_CUDA(cudaMemcpyAsync(d_member, member, (size_t)total * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(cudaMemcpyAsync(d_off, block_off, (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (B > 0) {
+        SD_CUDA(cudaMemcpyAsync(d_qpos, query_pos, (size_t)B * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (hull_volume) SD_CUDA(cudaMemcpyAsync(d_vol, hull_volume, (size_t)B * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    SD_TRY(mark(ctx, 1));
+    SD_TRY(cloud_blocks_device(ctx, dP, d, d_member, d_off, d_qpos, B, kind, tol, hull_volume ? d_vol : nullptr, d_out));
+    SD_TRY(mark(ctx, 2));
+    if (B > 0) SD_CUDA(cudaMemcpyAsync(out, d_out, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx, true);
 }
 
 int sd_band_depth_batched_f64(sd_ctx *ctx, const double *X, int64_t T, int64_t n, int64_t ld,

@@ -94,6 +94,9 @@ struct sd_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;                         // H2D of row blocks overlapped with ranking
     cudaEvent_t ev_pipe[4] = {nullptr, nullptr, nullptr, nullptr};  // copied[2], consumed[2]
+    void *stage[2] = {nullptr, nullptr};                        // pinned staging of pageable host input (api.cu)
+    size_t stage_cap[2] = {0, 0};
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // h2d start | kernels start | kernels end | d2h end
     sd_timings last = {0, 0, 0, 0, 0, 0};
     int bd_impl = SD_BD_AUTO;
@@ -148,6 +151,8 @@ int compact_batches_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, const i6
 int l1_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 nq, double *d_out);
 int oja_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 nq, const i64 *d_pool,
                i64 npool, double hull_volume, double *d_out);
+int cloud_blocks_device(sd_ctx *ctx, const double *dP, int d, const i64 *d_member, const i64 *d_off,
+                        const i64 *d_qpos, i64 B, int kind, double tol, const double *d_volume, double *d_out);
 int simplicial_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 nq, double tol,
                       i64 *d_out);
 int simplicial2_count_device(sd_ctx *ctx, const double *d_pts, i64 n, i64 stride_j, i64 T, const i64 *d_q, i64 nq,

@@ -261,6 +261,10 @@ int sd_destroy(sd_ctx *ctx) {
         if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
     for (int i = 0; i < 4; ++i)
         if (ctx->ev_pipe[i]) cudaEventDestroy(ctx->ev_pipe[i]);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
+        if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+    }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

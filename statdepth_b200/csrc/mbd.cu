@@ -416,9 +416,12 @@ __device__ __forceinline__ void emit_rank(const RankOut &o, i64 row_global, i64 
 
 // count = number of accumulator entries (n per group)
 __global__ void mbd_finish_kernel(const u64 *__restrict__ raw2, i64 *__restrict__ acc2, const i64 count,
-                                  const i64 rows_full2) {
+                                  const i64 rows_full2, const int accumulate) {
     const i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < count) acc2[c] += rows_full2 - (i64)(raw2[c] >> 1);
+    if (c < count) {
+        const i64 v = rows_full2 - (i64)(raw2[c] >> 1);
+        acc2[c] = accumulate ? acc2[c] + v : v;  // a fresh result needs no zeroing pass
+    }
 }
 
 // Runs of equal 22-bit keys in a sorted part (collisions of distinct values, or true ties).  The caller has
@@ -1226,9 +1229,9 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         set_error("mbd: neither an accumulator nor a rank output was given");
         return SD_ERR_INVALID;
     }
-    if (!accumulate && d_acc2) {
-        SD_CUDA(cudaMemsetAsync(d_acc2, 0, (size_t)acc_len * sizeof(i64), st));
+    if (!accumulate && d_acc2) {  // d_acc2 itself is WRITTEN by mbd_finish_kernel
         if (want_j3) SD_CUDA(cudaMemsetAsync(d_acc3, 0, (size_t)acc_len * sizeof(i64), st));
+        if (T == 0) SD_CUDA(cudaMemsetAsync(d_acc2, 0, (size_t)acc_len * sizeof(i64), st));
     }
     if (T == 0) return SD_OK;
 
@@ -1358,7 +1361,8 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     }
     if (d_acc2) {
         mbd_finish_kernel<<<(unsigned)ceil_div(acc_len, 256), 256, 0, st>>>(raw2, d_acc2, acc_len,
-                                                                            (group_rows > 0 ? group_rows : T) * o.full2);
+                                                                            (group_rows > 0 ? group_rows : T) * o.full2,
+                                                                            accumulate ? 1 : 0);
         ctx->last.launches++;
     }
     SD_CUDA(cudaGetLastError());

@@ -326,6 +326,133 @@ int oja_device(sd_ctx *ctx, const double *dP, i64 n, int d, const i64 *d_q, i64 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Blocks: B small sub-clouds of one cloud, ONE query each, in one launch.  This is what K-sampled point-cloud
+// depth is made of (_samplepointwisedepth, _pointcloud.py:97-123: len(to_compute) * ss blocks of ss or ss + 1
+// sampled points, each a single-query depth); the members of block b are member[off[b] .. off[b+1]) (ids into P,
+// in the order the reference holds them: the L1 sum runs in that order), its query is member[off[b] + qpos[b]].
+// One CTA per block; the sub-cloud is staged in shared memory when it fits.
+//   kind 0: simplicial count (as a double; exact below 2^53)   kind 1: L1 depth   kind 2: Oja sum / volume[b]
+// ---------------------------------------------------------------------------------------------
+constexpr int BLK_SMEM_DOUBLES = 4096;  // 32 KB: sub-clouds of up to 4096 / d points are staged
+
+template <int D>
+__global__ void __launch_bounds__(256) cloud_blocks_kernel(const double *__restrict__ P, const i64 *__restrict__ member,
+                                                           const i64 *__restrict__ off, const i64 *__restrict__ qpos,
+                                                           const int kind, const double tol,
+                                                           const double *__restrict__ volume, double *__restrict__ out) {
+    __shared__ double s_pts[BLK_SMEM_DOUBLES];
+    __shared__ u64 s_red[8];
+    __shared__ double s_redf[8];
+    const i64 b = blockIdx.x;
+    const i64 m0 = off[b], m = off[b + 1] - m0;  // members of this block
+    const i64 pq = qpos[b];
+    if (m * D > BLK_SMEM_DOUBLES) {  // host side refuses these; keep the kernel total
+        if (threadIdx.x == 0) out[b] = nan("");
+        return;
+    }
+    for (i64 i = threadIdx.x; i < m * D; i += blockDim.x) s_pts[i] = P[member[m0 + i / D] * D + i % D];
+    __syncthreads();
+    double xp[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) xp[c] = s_pts[pq * D + c];
+    if (kind == 1) {
+        // sequential sum in member order by ONE thread per coordinate would be the reference bit for bit; the blocks
+        // are small, so thread 0 does exactly that (sqrt and divisions as in _L1_depth, _pointcloud.py:145-146)
+        if (threadIdx.x == 0) {
+            double sum[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) sum[c] = 0.0;
+            for (i64 o = 0; o < m; ++o) {
+                if (o == pq) continue;
+                double nrm2 = 0.0, diff[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    diff[c] = s_pts[o * D + c] - xp[c];
+                    const double back = xp[c] - s_pts[o * D + c];
+                    nrm2 += back * back;
+                }
+                const double nrm = sqrt(nrm2);
+#pragma unroll
+                for (int c = 0; c < D; ++c) sum[c] += diff[c] / nrm;
+            }
+            double tot = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) tot += sum[c] * sum[c];
+            out[b] = 1.0 - sqrt(tot) / (double)m;
+        }
+        return;
+    }
+    const i64 mo = m - 1;  // others; position i of the "others" list skips the query
+    const i64 npairs = mo * (mo - 1) / 2;
+    u64 count = 0;
+    double acc = 0.0;
+    for (i64 pid = threadIdx.x; pid < npairs; pid += blockDim.x) {
+        i64 ia, ib;
+        unrank_pair(pid, ia, ib);
+        const i64 a = ia + (ia >= pq), bb = ib + (ib >= pq);
+        if (kind == 2) {
+            if (D == 2) {
+                acc += fabs(orient2(s_pts + a * 2, s_pts + bb * 2, xp)) / 2.0;
+            } else if (D == 3) {
+                for (i64 ic = ib + 1; ic < mo; ++ic) {
+                    const i64 c3 = ic + (ic >= pq);
+                    acc += fabs(orient3(s_pts + a * 3, s_pts + bb * 3, s_pts + c3 * 3, xp)) / 6.0;
+                }
+            }
+            continue;
+        }
+        double V[(D + 1) * D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            V[c] = s_pts[a * D + c];
+            V[D + c] = s_pts[bb * D + c];
+        }
+        if (D == 1) {
+            count += in_simplex<D>(V, xp, tol);
+        } else {
+            for (i64 ic = ib + 1; ic < mo; ++ic) {
+                const i64 c3 = ic + (ic >= pq);
+#pragma unroll
+                for (int c = 0; c < D; ++c) V[2 * D + c] = s_pts[c3 * D + c];
+                if (D == 2) {
+                    count += in_simplex<D>(V, xp, tol);
+                } else {
+                    for (i64 ie = ic + 1; ie < mo; ++ie) {
+                        const i64 c4 = ie + (ie >= pq);
+#pragma unroll
+                        for (int c = 0; c < D; ++c) V[3 * D + c] = s_pts[c4 * D + c];
+                        count += in_simplex<D>(V, xp, tol);
+                    }
+                }
+            }
+        }
+    }
+    if (kind == 2) {
+        const double tot = block_sum_f64(acc, s_redf);
+        if (threadIdx.x == 0) out[b] = tot / volume[b];
+    } else {
+        const u64 tot = block_sum_u64(count, s_red);
+        if (threadIdx.x == 0) out[b] = (double)tot;
+    }
+}
+
+int cloud_blocks_device(sd_ctx *ctx, const double *dP, int d, const i64 *d_member, const i64 *d_off,
+                        const i64 *d_qpos, i64 B, int kind, double tol, const double *d_volume, double *d_out) {
+    if (B == 0) return SD_OK;
+    cudaStream_t st = ctx->stream;
+    const unsigned grid = (unsigned)B;
+    switch (d) {
+        case 1: cloud_blocks_kernel<1><<<grid, 256, 0, st>>>(dP, d_member, d_off, d_qpos, kind, tol, d_volume, d_out); break;
+        case 2: cloud_blocks_kernel<2><<<grid, 256, 0, st>>>(dP, d_member, d_off, d_qpos, kind, tol, d_volume, d_out); break;
+        case 3: cloud_blocks_kernel<3><<<grid, 256, 0, st>>>(dP, d_member, d_off, d_qpos, kind, tol, d_volume, d_out); break;
+        default: set_error("point-cloud blocks: d=%d not supported (1..3)", d); return SD_ERR_UNSUPPORTED;
+    }
+    ctx->last.launches++;
+    SD_CUDA(cudaGetLastError());
+    return SD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // multivariate functional simplex depth numerator: one CTA per query curve; F[(i*T + t)*D + c]
 // ---------------------------------------------------------------------------------------------
 template <int D>

@@ -47,12 +47,17 @@ def _functionalhomogeneity(F: List[pd.DataFrame], G: List[pd.DataFrame], K=None,
             F_depths = FunctionalDepth([Fd], **kw)
             return np.abs(G_deep_in_F - F_depths.median().iloc[0])
         elif method == 'p3':
-            t = []
-            for col in Gd.columns:
-                Fc = Fd.copy()
-                Fc.loc[:, col] = Gd.loc[:, col].values
-                t.append(FunctionalDepth([Fc], to_compute=[col], K=K, J=J, containment=containment, relax=relax,
-                                         deep_check=deep_check).loc[col])
+            if K is None and containment == 'r2' and J in (2, 3) and not set(Gd.columns) & set(Fd.columns):
+                # the |G| single-query depth runs of the reference (homogeneity.py:121-133), each of one curve of G
+                # inside F u {that curve}, as ONE batched engine call on the pooled matrix
+                t = _depths_of_each_in(Fd, Gd, J, relax)
+            else:
+                t = []
+                for col in Gd.columns:
+                    Fc = Fd.copy()
+                    Fc.loc[:, col] = Gd.loc[:, col].values
+                    t.append(FunctionalDepth([Fc], to_compute=[col], K=K, J=J, containment=containment, relax=relax,
+                                             deep_check=deep_check).loc[col])
             depths_G_in_F = pd.Series(index=list(Gd.columns), data=t).sort_values(ascending=False)
             return depths_G_in_F.iloc[0] / G_depths.median().iloc[0]
         elif method == 'p4':
@@ -71,6 +76,28 @@ def _functionalhomogeneity(F: List[pd.DataFrame], G: List[pd.DataFrame], K=None,
         elif method == 'p3':
             return None  # the reference's branch is `pass`
         raise ValueError(_BAD_METHOD.format(method))
+
+
+def _depths_of_each_in(Fd: pd.DataFrame, Gd: pd.DataFrame, J: int, relax: bool) -> np.ndarray:
+    """depth of every column g of Gd inside Fd u {g}: |G| sub-populations of the pooled matrix, one batched call
+    per subset size j (sd_band_depth_batched_f64)."""
+    from scipy.special import binom
+
+    from . import _functional
+    eng = _functional.get_engine()
+    X = np.ascontiguousarray(np.concatenate([Fd.to_numpy(dtype=np.float64), Gd.to_numpy(dtype=np.float64)], axis=1))
+    T, nF, nG = X.shape[0], Fd.shape[1], Gd.shape[1]
+    mem = np.zeros((nG, nF + nG), dtype=np.uint8)
+    mem[:, :nF] = 1
+    mem[np.arange(nG), nF + np.arange(nG)] = 1
+    q = (nF + np.arange(nG, dtype=np.int64))[:, None]
+    depth = np.zeros(nG)
+    for j in range(2, J + 1):
+        s_nj = eng.band_depth_counts_batched(X, mem, q, j, relax)[:, 0].astype(np.float64)
+        if relax:
+            s_nj = s_nj / float(T)
+        depth = depth + s_nj / binom(nF + 1, j)
+    return depth
 
 
 def _pointcloudhomogeneity(F: pd.DataFrame, G: pd.DataFrame, K=None, containment='simplex', method='p1'):
@@ -170,7 +197,7 @@ def P2_homogeneity(F: pd.DataFrame, G: pd.DataFrame, K=None, J=2, containment='r
 
 
 def _perm_stats_batched(pooled: pd.DataFrame, nF: int, perms: np.ndarray, method: str, relax: bool) -> np.ndarray:
-    """p1 / p2 statistics of all permutations with two or three BATCHED engine calls
+    """p1 / p2 / p3 statistics of all permutations with two or three BATCHED engine calls
     (sd_band_depth_batched_f64: one launch sequence for all permutations) instead of 2-3 calls per
     permutation.  Same arithmetic and the same tie-breaking (pandas sort) as FunctionalHomogeneity."""
     from scipy.special import binom
@@ -207,6 +234,15 @@ def _perm_stats_batched(pooled: pd.DataFrame, nF: int, perms: np.ndarray, method
     g_in_F = depths(memF, deepest[:, None], np.full(B, nF + 1))[:, 0]
     if method == 'p1':
         return g_in_F
+    if method == 'p3':
+        # max over g in G_b of depth(g in F_b u {g}) / top depth of G_b in G_b: B * nG sub-populations, one call
+        memE = np.repeat(np.zeros((B, n), dtype=np.uint8), nG, axis=0)
+        rowsE = np.arange(B * nG)
+        memE[np.repeat(np.arange(B), nG)[:, None], np.repeat(perms[:, :nF], nG, axis=0)] = 1
+        gE = qG.reshape(-1)
+        memE[rowsE, gE] = 1
+        dE = depths(memE, gE[:, None], np.full(B * nG, nF + 1))[:, 0].reshape(B, nG)
+        return dE.max(axis=1) / dG.max(axis=1)  # `.median()` of the reference's result types is the DEEPEST curve
     # (3) p2: | depth(g in F u {g}) - max depth of F_b in F_b |
     memF0 = np.zeros((B, n), dtype=np.uint8)
     memF0[rows, perms[:, :nF]] = 1
@@ -240,7 +276,7 @@ def permutation_test(F: pd.DataFrame, G: pd.DataFrame, method='p1', B=200, seed=
 
     def run(block):
         block = list(block)
-        if batched and method in ('p1', 'p2') and J == 2 and containment == 'r2' and block:
+        if batched and method in ('p1', 'p2', 'p3') and J == 2 and containment == 'r2' and block:
             return _perm_stats_batched(pooled, nF, perms[block], method, relax)
         return np.array([stat(pooled.iloc[:, perms[b][:nF]], pooled.iloc[:, perms[b][nF:]]) for b in block])
 

@@ -42,3 +42,36 @@ def check_case(case, FunctionalDepth, PointcloudDepth, rtol=1e-12):
             assert [int(i) for i in res.index] == case["index"]
     else:
         raise AssertionError(kind)
+
+
+def load_next_cases():
+    """tests/golden/reference_vectors_next.json: K-sampled point clouds, point-cloud homogeneity, Mahalanobis."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_next.json")) as fh:
+        return json.load(fh)["cases"]
+
+
+def check_next_case(case, PointcloudDepth, PointcloudHomogeneity, rtol=1e-12):
+    """SURVEY 8(f) rows against the unmodified reference's outputs."""
+    kind = case["kind"]
+    if kind == "pointcloud_K":
+        np.random.seed(case["np_seed"])  # the reference samples blocks from the GLOBAL numpy RNG (_pointcloud.py:114)
+        res = PointcloudDepth(pd.DataFrame(np.array(case["P"])), K=case["K"], containment=case["containment"],
+                              to_compute=case.get("to_compute"))
+        assert [int(i) for i in res.index] == case["index"]
+        np.testing.assert_allclose(res.values, case["depths"], rtol=rtol, atol=1e-15)
+    elif kind == "pointcloud_homogeneity":
+        F = pd.DataFrame(np.array(case["F"]), index=["F%d" % i for i in range(len(case["F"]))])
+        G = pd.DataFrame(np.array(case["G"]), index=["G%d" % i for i in range(len(case["G"]))])
+        h = PointcloudHomogeneity(F, G, method=case["method"], containment=case["containment"])
+        np.testing.assert_allclose(float(h.homogeneity()), case["value"], rtol=rtol)
+        np.testing.assert_allclose(h.F_depths().values, case["F_depths"], rtol=rtol, atol=1e-15)
+        np.testing.assert_allclose(h.G_depths().values, case["G_depths"], rtol=rtol, atol=1e-15)
+        assert list(F.index) == ["F%d" % i for i in range(len(case["F"]))]  # the caller's F is not mutated
+    elif kind == "mahalanobis":
+        res = PointcloudDepth(pd.DataFrame(np.array(case["P"])), containment="mahalanobis",
+                              to_compute=case.get("to_compute"))
+        np.testing.assert_allclose(res.values, case["depths"], rtol=1e-9)  # n == p: inverse of a singular covariance
+    else:
+        raise AssertionError(kind)

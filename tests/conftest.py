@@ -75,6 +75,19 @@ class OracleBackedEngine:
     def l1_depth(self, P, queries=None):
         return self.o.l1_depth(P, queries)
 
+    def cloud_blocks(self, P, members, offsets, query_pos, kind, tol=1e-7, hull_volumes=None):
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        out = np.zeros(len(query_pos))
+        for b, qp in enumerate(query_pos):
+            sub = np.ascontiguousarray(P[np.asarray(members[offsets[b]:offsets[b + 1]], dtype=np.int64)])
+            if kind == "simplex":
+                out[b] = self.o.simplicial_counts(sub, [qp], tol)[0]
+            elif kind == "l1":
+                out[b] = self.o.l1_depth(sub, [qp])[0]
+            else:
+                out[b] = self.o.oja(sub, hull_volumes[b], [qp])[0]
+        return out
+
     def oja(self, P, hull_volume, queries=None, pool=None):
         return self.o.oja(P, hull_volume, queries, pool)
 

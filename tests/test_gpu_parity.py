@@ -733,3 +733,51 @@ def test_homogeneity_and_permutation_test(golden):
         a = permutation_test(F, G, method=method, B=10, seed=6, relax=False)
         b = permutation_test(F, G, method=method, B=10, seed=6, relax=False, batched=False)
         assert a["null"].tolist() == b["null"].tolist()
+
+
+def test_next_rows_against_the_reference_on_gpu():
+    """K-sampled point-cloud depth through sd_pointcloud_blocks_f64, point-cloud homogeneity p1..p3,
+    Mahalanobis -- the unmodified reference's outputs (tests/golden/make_golden_next.py)."""
+    from api_cases import check_next_case, load_next_cases
+    from statdepth_b200 import PointcloudDepth
+    from statdepth_b200.homogeneity import PointcloudHomogeneity
+    for case in load_next_cases():
+        check_next_case(case, PointcloudDepth, PointcloudHomogeneity, rtol=RTOL)
+
+
+def test_cloud_blocks_abi(engine, oracle):
+    """sd_pointcloud_blocks_f64: ragged blocks, all three kinds, d = 2 and 3, against single-cloud oracle calls."""
+    rng = np.random.default_rng(61)
+    for d in (2, 3):
+        P = rng.standard_normal((40, d))
+        members, offsets, qpos, hv = [], [0], [], []
+        for b in range(23):
+            m = int(rng.integers(d + 2, 15))
+            ids = rng.choice(40, m, replace=False)
+            members.append(ids)
+            offsets.append(offsets[-1] + m)
+            qpos.append(int(rng.integers(0, m)))
+            hv.append(float(rng.uniform(0.5, 2.0)))
+        mem = np.concatenate(members)
+        for kind in ("simplex", "l1", "oja"):
+            got = engine.cloud_blocks(P, mem, offsets, qpos, kind, 1e-7, hv)
+            for b in range(23):
+                sub = np.ascontiguousarray(P[members[b]])
+                if kind == "simplex":
+                    assert got[b] == oracle.simplicial_counts(sub, [qpos[b]])[0]
+                elif kind == "l1":
+                    assert got[b] == oracle.l1_depth(sub, [qpos[b]])[0]  # same operations in the same order
+                else:
+                    np.testing.assert_allclose(got[b], oracle.oja(sub, hv[b], [qpos[b]])[0], rtol=RTOL)
+
+
+def test_permutation_test_p3_batched(engine):
+    from statdepth_b200.homogeneity import permutation_test
+    rng = np.random.default_rng(8)
+    F = pd.DataFrame(rng.standard_normal((24, 14)).cumsum(0))
+    G = pd.DataFrame(rng.standard_normal((24, 14)).cumsum(0) + 1.0)
+    for relax in (True, False):
+        a = permutation_test(F, G, method="p3", B=6, seed=2, relax=relax)
+        b = permutation_test(F, G, method="p3", B=6, seed=2, relax=relax, batched=False)
+        np.testing.assert_allclose(a["null"], b["null"], rtol=RTOL)
+        assert a["observed"] == b["observed"]

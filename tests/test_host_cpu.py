@@ -5,7 +5,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from api_cases import check_case
+from api_cases import check_case, check_next_case, load_next_cases
 from statdepth_b200 import DepthDegeneracy, EngineUnavailable, FunctionalDepth, PointcloudDepth
 from statdepth_b200.homogeneity import FunctionalHomogeneity, P1_homogeneity, P2_homogeneity
 from statdepth_b200.testing import (generate_noisy_multivariate, generate_noisy_pointcloud,
@@ -171,3 +171,31 @@ def test_enumeration_guard(host_on_oracle):
         assert len(PointcloudDepth(pd.DataFrame(rng.standard_normal((12, 2))), containment='simplex')) == 12
     finally:
         settings.set_max_enumeration(old)
+
+
+def test_next_rows_against_the_reference(host_on_oracle):
+    """K-sampled point-cloud depth (blocks replayed from the global RNG, one batched call), point-cloud
+    homogeneity p1..p3 and Mahalanobis depth: outputs of the unmodified reference (make_golden_next.py)."""
+    from statdepth_b200.homogeneity import PointcloudHomogeneity
+    cases = load_next_cases()
+    assert len(cases) >= 12
+    for case in cases:
+        check_next_case(case, PointcloudDepth, PointcloudHomogeneity)
+
+
+def test_functional_p3_batched_equals_loop(host_on_oracle, golden):
+    """p3 evaluates its |G| single-query depth runs as one batched call; K forces the reference's loop."""
+    case = golden["functional_p3"]
+    F = pd.DataFrame(np.array(case["F"]), columns=["F%d" % i for i in range(7)])
+    G = pd.DataFrame(np.array(case["G"]), columns=["G%d" % i for i in range(6)])
+    h = FunctionalHomogeneity([F], [G], method="p3", quiet=True).homogeneity()
+    np.testing.assert_allclose(float(np.asarray(h).ravel()[0]), case["value"], rtol=1e-12)
+    for relax in (True, False):
+        from statdepth_b200 import homogeneity as H
+        batched = H._depths_of_each_in(F, G, 3, relax)
+        loop = []
+        for col in G.columns:
+            Fc = F.copy()
+            Fc.loc[:, col] = G.loc[:, col].values
+            loop.append(FunctionalDepth([Fc], to_compute=[col], J=3, relax=relax).loc[col])
+        np.testing.assert_allclose(batched, loop, rtol=1e-13)
