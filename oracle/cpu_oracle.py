@@ -193,3 +193,17 @@ def simplex2_relaxed_counts_arcs(F, queries=None, tol=1e-7):
     if rc:
         raise RuntimeError("sdo_triangle_counts_arcs rc=%d" % rc)
     return out
+
+
+def simplex2_strict_fast(F, queries=None, tol=1e-7):
+    """Strict multivariate simplex numerator (d = 2) with an exact pre-test per (triple, row): for config-4 sizes."""
+    F = _c64(F)
+    N, T, d = F.shape
+    assert d == 2
+    q = _q(queries, N)
+    out = np.zeros(q.size, dtype=np.int64)
+    rc = lib().sdo_simplex2_strict_fast(F.ctypes.data_as(_f64p), C.c_int64(N), C.c_int64(T), q.ctypes.data_as(_i64p),
+                                        C.c_int64(q.size), C.c_double(tol), out.ctypes.data_as(_i64p))
+    if rc:
+        raise RuntimeError("sdo_simplex2_strict_fast rc=%d" % rc)
+    return out

@@ -658,3 +658,67 @@ SDO_EXPORT int sdo_triangle_counts_arcs(const double *pts, i64 n, i64 stride, i6
     arcs_ctx c = {pts, n, stride, T, q, tol, out};
     return parallel_for(nq, 1, arcs_body, &c, (size_t)(2 * n) * sizeof(double));
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Strict multivariate simplex depth numerator, d = 2, at sizes the plain transcription (sx_body) cannot reach
+ * (BASELINE config 4: C(4999,3) triples per query).  Same definition -- #triples of other curves whose closed
+ * triangle (tolerance band tol, sdo_in_simplex) contains the query at ALL T rows -- with a cheap exact pre-test
+ * per (triple, row): the three edge functions of the triangle as seen from the query; all clearly of one sign ->
+ * inside; one clearly negative beyond tol * (upper bound of the edge length) -> outside; anything else is decided
+ * by sdo_in_simplex itself.  Checked against sdo_simplex_depth_counts in tests/test_oracle.py.
+ * Work is split over (query, first vertex) so that a few queries use all host threads.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { const double *F; i64 N, T; const i64 *q; i64 nq; double tol; atomic_llong *acc; } sxf_ctx;
+
+static inline int sxf_classify(double e0, double e1, double e2, double ra, double rb, double rc, double tol) {
+    const double kE = 1e-12, pab = ra * rb, pbc = rb * rc, pca = rc * ra;
+    if ((e0 > kE * pab && e1 > kE * pbc && e2 > kE * pca) || (e0 < -kE * pab && e1 < -kE * pbc && e2 < -kE * pca)) return 1;
+    const double D = (e0 + e1) + e2, big = kE * (pab + pbc + pca);
+    const double m0 = tol * (ra + rb) * (1.0 + 1e-9) + kE * pab, m1 = tol * (rb + rc) * (1.0 + 1e-9) + kE * pbc,
+                 m2 = tol * (rc + ra) * (1.0 + 1e-9) + kE * pca;
+    if (D > big && (e0 < -m0 || e1 < -m1 || e2 < -m2)) return -1;
+    if (D < -big && (e0 > m0 || e1 > m1 || e2 > m2)) return -1;
+    return 0;
+}
+
+static int sxf_inside(const double *F, i64 T, i64 t, i64 a, i64 b, i64 c, i64 qc, double tol) {
+    const double *pa = F + (a * T + t) * 2, *pb = F + (b * T + t) * 2, *pc = F + (c * T + t) * 2, *pp = F + (qc * T + t) * 2;
+    const double vax = pa[0] - pp[0], vay = pa[1] - pp[1], vbx = pb[0] - pp[0], vby = pb[1] - pp[1],
+                 vcx = pc[0] - pp[0], vcy = pc[1] - pp[1];
+    const double e0 = vax * vby - vay * vbx, e1 = vbx * vcy - vby * vcx, e2 = vcx * vay - vcy * vax;
+    const double up = 1.0 + 1e-7;
+    const int cls = sxf_classify(e0, e1, e2, sqrt(vax * vax + vay * vay) * up, sqrt(vbx * vbx + vby * vby) * up,
+                                 sqrt(vcx * vcx + vcy * vcy) * up, tol);
+    if (cls) return cls > 0;
+    double V[6] = {pa[0], pa[1], pb[0], pb[1], pc[0], pc[1]};
+    return sdo_in_simplex(V, 2, pp, tol);
+}
+
+static void sxf_body(i64 job, void *vctx, void *scratch) {
+    (void)scratch;
+    sxf_ctx *x = (sxf_ctx *)vctx;
+    const i64 N = x->N, T = x->T, qi = job / N, a = job % N, qc = x->q[qi];
+    if (a == qc) return;
+    i64 cnt = 0;
+    for (i64 b = a + 1; b < N; ++b) {
+        if (b == qc) continue;
+        for (i64 c = b + 1; c < N; ++c) {
+            if (c == qc) continue;
+            int all = 1;
+            for (i64 t = 0; t < T && all; ++t) all = sxf_inside(x->F, T, t, a, b, c, qc, x->tol);
+            cnt += all;
+        }
+    }
+    atomic_fetch_add(&x->acc[qi], cnt);
+}
+
+SDO_EXPORT int sdo_simplex2_strict_fast(const double *F, i64 N, i64 T, const i64 *q, i64 nq, double tol, i64 *out) {
+    if (N < 1 || T < 1 || !(tol >= 0.0)) return -1;
+    atomic_llong *acc = (atomic_llong *)calloc((size_t)(nq > 0 ? nq : 1), sizeof(atomic_llong));
+    if (!acc) return -2;
+    sxf_ctx c = {F, N, T, q, nq, tol, acc};
+    const int rc = parallel_for(nq * N, 1, sxf_body, &c, 0);
+    for (i64 i = 0; i < nq; ++i) out[i] = (i64)atomic_load(&acc[i]);
+    free(acc);
+    return rc;
+}

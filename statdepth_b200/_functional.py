@@ -78,7 +78,14 @@ def _multivariate_depths(data: List[pd.DataFrame], queries: np.ndarray, relax: b
     if d > 3:
         raise NotImplementedError('simplex containment is implemented for d <= 3 channels on the B200 engine')
     tol = settings.get_simplex_tolerance()
-    if not (d == 2 and relax and N > 64):  # relaxed 2-D depth above 64 curves is counted per (query, time point)
+    if d == 2 and relax and N > 64:
+        pass  # relaxed 2-D depth above 64 curves is COUNTED per (query, time point): O(N log N) each
+    elif d == 2 and not relax:
+        # strict 2-D depth is enumerated with first-row pruning in shared memory (~1.3 cheap tests per triple,
+        # csrc/pointcloud.cu simplex2_strict_kernel): config 4 (5 000 queries x C(4999,3) triples) runs in minutes
+        settings.check_enumeration(float(len(queries)) * binom(N - 1, 3) / 4.0,
+                                   'strict multivariate simplex depth (d=2, N=%d)' % N)
+    else:
         settings.check_enumeration(float(len(queries)) * binom(N - 1, d + 1) * (T if relax else 1.0),
                                    'multivariate simplex depth (d=%d, N=%d, relax=%s)' % (d, N, relax))
     cnt = _dist.query_sharded(lambda qb: eng.simplex_depth_counts(F, qb, relax, tol), queries, np.int64)

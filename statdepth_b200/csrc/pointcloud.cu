@@ -509,6 +509,114 @@ __global__ void __launch_bounds__(256) simplex_depth_kernel(const double *__rest
     if (threadIdx.x == 0) out[blockIdx.x] = (i64)tot;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Strict multivariate simplex depth, d = 2, for samples the plain enumeration above cannot finish (BASELINE
+// config 4: 5 000 curves x 256 points -> C(4999,3) = 2.1e10 triples per query).  A triple counts iff the query lies
+// in its closed triangle (tolerance band tol) at ALL T rows, so one row prunes: the directions v_o = x_o - x_q of
+// the FIRST row are staged in shared memory (two doubles and a float upper bound of |v_o| per curve), every thread
+// takes pairs (a, b) and streams c > b through two cross products.  With e_k = the three edge functions,
+//     all e_k  >  +eps_k                          -> inside at this row for certain (any tolerance)
+//     some e_k < -tol (|v_i| + |v_j|) - eps_k     -> farther than tol from that edge's line: outside for certain
+// (|x_i - x_j| <= |v_i| + |v_j|; eps_k = 1e-12 |v_i| |v_j| covers the rounding of the cross product), and only the
+// rest -- within the band of an edge, or degenerate -- is decided by the reference predicate in_simplex<2> itself.
+// Survivors (at most a quarter of the triples on average) walk the remaining rows with early exit, same three
+// cases, vertices read through L2.  Decisions are therefore exactly those of the enumeration kernel / the oracle.
+// ---------------------------------------------------------------------------------------------
+constexpr int SX_THREADS = 512;
+struct SxPoint { double x, y; float r; float pad; };  // 24 bytes
+
+__device__ __forceinline__ int sx_classify(const double e0, const double e1, const double e2, const float ra,
+                                           const float rb, const float rc, const double tol) {
+    // +1 inside for certain, -1 outside for certain, 0 ask the predicate
+    const double pab = (double)ra * (double)rb, pbc = (double)rb * (double)rc, pca = (double)rc * (double)ra;
+    const double kE = 1e-12;
+    const bool pos = e0 > kE * pab && e1 > kE * pbc && e2 > kE * pca;
+    const bool neg = e0 < -kE * pab && e1 < -kE * pbc && e2 < -kE * pca;
+    if (pos || neg) return 1;
+    // orientation of the triangle = sign of e0 + e1 + e2; an edge function of the opposite sign, beyond the band
+    const double D = (e0 + e1) + e2;
+    const double m0 = tol * ((double)ra + (double)rb) * (1.0 + 1e-9) + kE * pab;
+    const double m1 = tol * ((double)rb + (double)rc) * (1.0 + 1e-9) + kE * pbc;
+    const double m2 = tol * ((double)rc + (double)ra) * (1.0 + 1e-9) + kE * pca;
+    const double big = kE * (pab + pbc + pca);
+    if (D > big && (e0 < -m0 || e1 < -m1 || e2 < -m2)) return -1;
+    if (D < -big && (e0 > m0 || e1 > m1 || e2 > m2)) return -1;
+    return 0;
+}
+
+__global__ void __launch_bounds__(SX_THREADS) simplex2_strict_kernel(const double *__restrict__ F, const i64 N, const i64 T,
+                                                                     const i64 *__restrict__ q, const double tol,
+                                                                     i64 *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char sx_smem[];
+    SxPoint *pt = reinterpret_cast<SxPoint *>(sx_smem);                 // [m] others at row 0
+    double *pq = reinterpret_cast<double *>(pt + (N - 1));               // [T][2] the query curve
+    __shared__ u64 s_red[SX_THREADS / 32];
+    const i64 qi = blockIdx.y;
+    const i64 qc = q ? q[qi] : qi;
+    const i64 m = N - 1;
+    for (i64 i = threadIdx.x; i < 2 * T; i += blockDim.x) pq[i] = F[qc * T * 2 + i];
+    __syncthreads();
+    for (i64 i = threadIdx.x; i < m; i += blockDim.x) {
+        const i64 o = i + (i >= qc);
+        const double vx = F[o * T * 2] - pq[0], vy = F[o * T * 2 + 1] - pq[1];
+        SxPoint p;
+        p.x = vx;
+        p.y = vy;
+        p.r = __double2float_ru(sqrt(vx * vx + vy * vy) * (1.0 + 1e-7));  // upper bound of |v|
+        p.pad = 0.f;
+        pt[i] = p;
+    }
+    __syncthreads();
+    u64 count = 0;
+    const i64 npairs = m * (m - 1) / 2;
+    for (i64 pid = (i64)blockIdx.x * blockDim.x + threadIdx.x; pid < npairs; pid += (i64)gridDim.x * blockDim.x) {
+        i64 ia, ib;
+        unrank_pair(pid, ia, ib);
+        const SxPoint A = pt[ia], B = pt[ib];
+        const double e0 = A.x * B.y - A.y * B.x;  // orient2(p, a, b)
+        const i64 oa = ia + (ia >= qc), ob = ib + (ib >= qc);
+        for (i64 ic = ib + 1; ic < m; ++ic) {
+            const SxPoint C = pt[ic];
+            const double e1 = B.x * C.y - B.y * C.x;  // orient2(p, b, c)
+            const double e2 = C.x * A.y - C.y * A.x;  // orient2(p, c, a)
+            int cls = sx_classify(e0, e1, e2, A.r, B.r, C.r, tol);
+            if (cls < 0) continue;
+            const i64 oc = ic + (ic >= qc);
+            if (cls == 0) {
+                double V[6];
+                V[0] = F[oa * T * 2]; V[1] = F[oa * T * 2 + 1];
+                V[2] = F[ob * T * 2]; V[3] = F[ob * T * 2 + 1];
+                V[4] = F[oc * T * 2]; V[5] = F[oc * T * 2 + 1];
+                if (!in_simplex<2>(V, pq, tol)) continue;
+            }
+            // remaining rows, early exit
+            bool all = true;
+            for (i64 t = 1; t < T; ++t) {
+                const double px = pq[2 * t], py = pq[2 * t + 1];
+                const double ax = F[(oa * T + t) * 2], ay = F[(oa * T + t) * 2 + 1];
+                const double bx = F[(ob * T + t) * 2], by = F[(ob * T + t) * 2 + 1];
+                const double cx = F[(oc * T + t) * 2], cy = F[(oc * T + t) * 2 + 1];
+                const double vax = ax - px, vay = ay - py, vbx = bx - px, vby = by - py, vcx = cx - px, vcy = cy - py;
+                const double f0 = vax * vby - vay * vbx, f1 = vbx * vcy - vby * vcx, f2 = vcx * vay - vcy * vax;
+                const float ra = __double2float_ru(sqrt(vax * vax + vay * vay) * (1.0 + 1e-7));
+                const float rb = __double2float_ru(sqrt(vbx * vbx + vby * vby) * (1.0 + 1e-7));
+                const float rc = __double2float_ru(sqrt(vcx * vcx + vcy * vcy) * (1.0 + 1e-7));
+                const int c2 = sx_classify(f0, f1, f2, ra, rb, rc, tol);
+                if (c2 > 0) continue;
+                bool in = false;
+                if (c2 == 0) {
+                    const double V[6] = {ax, ay, bx, by, cx, cy}, P2[2] = {px, py};
+                    in = in_simplex<2>(V, P2, tol);
+                }
+                if (!in) { all = false; break; }
+            }
+            count += all;
+        }
+    }
+    const u64 tot = block_sum_u64(count, s_red);
+    if (threadIdx.x == 0 && tot) atomicAdd((u64 *)&out[qi], tot);
+}
+
 int simplex_depth_device(sd_ctx *ctx, const double *dF, i64 N, i64 T, int d, const i64 *d_q, i64 nq, int relax,
                          double tol, i64 *d_out) {
     if (nq == 0) return SD_OK;
@@ -517,6 +625,25 @@ int simplex_depth_device(sd_ctx *ctx, const double *dF, i64 N, i64 T, int d, con
                             (ctx->simplicial_impl == SD_SIMPLICIAL_AUTO && N > SIMPLEX_ENUM_MAX_N)))
         return simplicial2_count_device(ctx, dF, N, 2 * T, T, d_q, nq, tol, d_out);
     cudaStream_t st = ctx->stream;
+    const size_t sx_bytes = (size_t)(N - 1) * sizeof(SxPoint) + (size_t)T * 2 * sizeof(double);
+    if (d == 2 && !relax && N >= 4 && sx_bytes <= 200 * 1024) {
+        // first-row pruning in shared memory; several CTAs per query so that a handful of queries fills the GPU
+        SD_CUDA(cudaFuncSetAttribute(simplex2_strict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sx_bytes));
+        SD_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nq * sizeof(i64), st));
+        const i64 npairs = (N - 1) * (N - 2) / 2;
+        i64 slices = ceil_div(npairs, (i64)SX_THREADS * 8);
+        const i64 want = ceil_div(2 * (i64)ctx->sm_count, nq);
+        if (slices > want) slices = want;
+        if (slices < 1) slices = 1;
+        for (i64 q0 = 0; q0 < nq; q0 += 65535) {
+            const i64 nb = nq - q0 < 65535 ? nq - q0 : 65535;
+            simplex2_strict_kernel<<<dim3((unsigned)slices, (unsigned)nb), SX_THREADS, sx_bytes, st>>>(
+                dF, N, T, d_q ? d_q + q0 : nullptr, tol, d_out + q0);
+            ctx->last.launches++;
+        }
+        SD_CUDA(cudaGetLastError());
+        return SD_OK;
+    }
     const unsigned grid = (unsigned)nq;
     switch (d) {
         case 1: simplex_depth_kernel<1><<<grid, 256, 0, st>>>(dF, N, T, d_q, relax, tol, d_out); break;

@@ -236,10 +236,10 @@ def _perm_stats_batched(pooled: pd.DataFrame, nF: int, perms: np.ndarray, method
         return g_in_F
     if method == 'p3':
         # max over g in G_b of depth(g in F_b u {g}) / top depth of G_b in G_b: B * nG sub-populations, one call
-        memE = np.repeat(np.zeros((B, n), dtype=np.uint8), nG, axis=0)
+        memE = np.zeros((B * nG, n), dtype=np.uint8)
         rowsE = np.arange(B * nG)
-        memE[np.repeat(np.arange(B), nG)[:, None], np.repeat(perms[:, :nF], nG, axis=0)] = 1
-        gE = qG.reshape(-1)
+        memE[rowsE[:, None], np.repeat(perms[:, :nF], nG, axis=0)] = 1  # row b * nG + k: F_b ...
+        gE = qG.reshape(-1)                                              # ... plus the k-th curve of G_b
         memE[rowsE, gE] = 1
         dE = depths(memE, gE[:, None], np.full(B * nG, nF + 1))[:, 0].reshape(B, nG)
         return dE.max(axis=1) / dG.max(axis=1)  # `.median()` of the reference's result types is the DEEPEST curve

@@ -781,3 +781,47 @@ def test_permutation_test_p3_batched(engine):
         b = permutation_test(F, G, method="p3", B=6, seed=2, relax=relax, batched=False)
         np.testing.assert_allclose(a["null"], b["null"], rtol=RTOL)
         assert a["observed"] == b["observed"]
+
+
+def test_strict_simplex_depth_d2_pruned_kernel(engine, oracle):
+    """Strict multivariate simplex depth, d = 2 (first-row pruning in shared memory, exact pre-test, reference
+    predicate inside the band): equals the oracle's plain enumeration on random walks, a lattice (collinear and
+    on-edge cases), the reference's collinear fixture, several tolerances and query subsets."""
+    from statdepth_b200.testing import generate_noisy_multivariate
+    rng = np.random.default_rng(4)
+    for N, T in ((5, 3), (12, 5), (40, 3), (90, 6), (150, 4)):
+        F = rng.standard_normal((N, T, 2)).cumsum(1) * (0.2 if N == 150 else 1.0)
+        for tol in (0.0, 1e-7, 0.05):
+            assert (engine.simplex_depth_counts(F, None, False, tol) == oracle.simplex_depth_counts(F, None, False, tol)).all()
+    Fl = rng.integers(0, 4, size=(25, 4, 2)).astype(np.float64)
+    assert (engine.simplex_depth_counts(Fl, None, False) == oracle.simplex_depth_counts(Fl, None, False)).all()
+    data = generate_noisy_multivariate(num_curves=70, n=5, d=2, seed=1)
+    Fd = np.stack([x.values for x in data])
+    got = engine.simplex_depth_counts(Fd, None, False)
+    assert (got == oracle.simplex_depth_counts(Fd, None, False)).all() and got.max() > 0
+    q = [3, 0, 69]
+    assert (engine.simplex_depth_counts(Fd, q, False) == got[q]).all()
+    F = rng.standard_normal((600, 16, 2)).cumsum(1)   # mid size against the oracle's pre-tested enumeration
+    q = [0, 299, 599]
+    assert (engine.simplex_depth_counts(F, q, False) == oracle.simplex2_strict_fast(F, q)).all()
+
+
+def _config4_strict_data():
+    """5 000 curves x 256 points x 2 channels: random walks, plus 14 far 'anchor' curves on a big circle so that the
+    strict depth of an inner curve is not simply 0 (only anchor triangles contain it at all 256 rows)."""
+    rng = np.random.default_rng(3)
+    F = rng.standard_normal((5000, 256, 2)).cumsum(1)
+    ang = np.sort(rng.uniform(0, 2 * np.pi, 14))
+    F[:14] = 2000.0 * np.stack([np.cos(ang), np.sin(ang)], axis=1)[:, None, :] + rng.standard_normal((14, 256, 2))
+    return F
+
+
+def test_config4_strict_depth_full_size(engine, oracle):
+    """BASELINE config 4, strict, d = 2, FULL size: one query (C(4999,3) = 2.1e10 triples) pinned by the oracle's
+    multi-threaded enumeration (about a minute of host time), plus 16 more queries for bounds and timing."""
+    F = _config4_strict_data()
+    got = engine.simplex_depth_counts(F, [2500], False)
+    exp = oracle.simplex2_strict_fast(F, [2500])
+    assert got.tolist() == exp.tolist() and got[0] > 0
+    more = engine.simplex_depth_counts(F, list(range(100, 4900, 300)), False)
+    assert more.min() >= 0 and more.max() <= comb(13, 3) + comb(13, 2) * 4986  # at most: triangles with >= 2 anchors

@@ -165,7 +165,7 @@ def test_enumeration_guard(host_on_oracle):
             PointcloudDepth(pd.DataFrame(rng.standard_normal((30, 3))), containment='simplex')
         with pytest.raises(NotImplementedError, match='enumerate'):
             PointcloudDepth(pd.DataFrame(rng.standard_normal((60, 2))), containment='oja')
-        curves = [pd.DataFrame(rng.standard_normal((4, 2))) for _ in range(20)]
+        curves = [pd.DataFrame(rng.standard_normal((4, 2))) for _ in range(40)]
         with pytest.raises(NotImplementedError, match='enumerate'):
             FunctionalDepth(curves, containment='simplex', relax=False)
         assert len(PointcloudDepth(pd.DataFrame(rng.standard_normal((12, 2))), containment='simplex')) == 12

@@ -171,3 +171,18 @@ def test_large_golden_vs_oracle(oracle):
             for c in (oracle.simplex_depth_counts(F, q, True), oracle.simplex2_relaxed_counts_arcs(F, q)):
                 np.testing.assert_allclose(c / T / comb(N - 1, 3), case["depths"], rtol=1e-12, atol=1e-15,
                                            err_msg=name)
+
+
+def test_strict_fast_oracle_equals_enumeration(oracle):
+    """The pre-tested strict enumeration used to pin config 4 at full size equals the plain transcription."""
+    from statdepth_b200.testing import generate_noisy_multivariate
+    rng = np.random.default_rng(4)
+    for N, T in ((12, 5), (40, 3), (60, 6)):
+        F = rng.standard_normal((N, T, 2)).cumsum(1)
+        for tol in (0.0, 1e-7, 0.05):
+            assert (oracle.simplex2_strict_fast(F, None, tol) == oracle.simplex_depth_counts(F, None, False, tol)).all()
+    Fl = rng.integers(0, 4, size=(20, 4, 2)).astype(np.float64)
+    assert (oracle.simplex2_strict_fast(Fl) == oracle.simplex_depth_counts(Fl, None, False)).all()
+    data = generate_noisy_multivariate(num_curves=30, n=5, d=2, seed=1)
+    F = np.stack([x.values for x in data])
+    assert (oracle.simplex2_strict_fast(F) == oracle.simplex_depth_counts(F, None, False)).all()
