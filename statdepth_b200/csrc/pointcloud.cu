@@ -512,106 +512,176 @@ __global__ void __launch_bounds__(256) simplex_depth_kernel(const double *__rest
 // ---------------------------------------------------------------------------------------------
 // Strict multivariate simplex depth, d = 2, for samples the plain enumeration above cannot finish (BASELINE
 // config 4: 5 000 curves x 256 points -> C(4999,3) = 2.1e10 triples per query).  A triple counts iff the query lies
-// in its closed triangle (tolerance band tol) at ALL T rows, so one row prunes: the directions v_o = x_o - x_q of
-// the FIRST row are staged in shared memory (two doubles and a float upper bound of |v_o| per curve), every thread
-// takes pairs (a, b) and streams c > b through two cross products.  With e_k = the three edge functions,
+// in its closed triangle (tolerance band tol) at ALL T rows, so every row prunes: the directions v_o = x_o - x_q of
+// the first SX_ROWS rows are staged in shared memory as floats (x, y and an upper bound r of |v_o|: 12 bytes per
+// curve and row, 180 KB at N = 5000), every thread takes pairs (a, b) and streams c > b through two float cross
+// products per staged row.  With e_k = the three edge functions of the triangle seen from the query,
 //     all e_k  >  +eps_k                          -> inside at this row for certain (any tolerance)
-//     some e_k < -tol (|v_i| + |v_j|) - eps_k     -> farther than tol from that edge's line: outside for certain
-// (|x_i - x_j| <= |v_i| + |v_j|; eps_k = 1e-12 |v_i| |v_j| covers the rounding of the cross product), and only the
-// rest -- within the band of an edge, or degenerate -- is decided by the reference predicate in_simplex<2> itself.
-// Survivors (at most a quarter of the triples on average) walk the remaining rows with early exit, same three
-// cases, vertices read through L2.  Decisions are therefore exactly those of the enumeration kernel / the oracle.
+//     some e_k < -tol (r_i + r_j) - eps_k         -> farther than tol from that edge's line: outside for certain
+// (|x_i - x_j| <= |v_i| + |v_j|; eps_k = 1e-6 r_i r_j covers the float rounding of v and of the cross product, 1e-12
+// r_i r_j for the float64 rows), and only the rest -- within the band of an edge, or degenerate -- is decided by the
+// reference predicate in_simplex<2> itself on the float64 vertices.  A triple survives a row with probability
+// <= 1/4 on average, so 1.6 % reach the remaining rows, which are walked in float64 through L2 with early exit (the
+// first version staged one row only and spent its time on the 25 % survivors' L2 reads: 312 ms per query).
+// Decisions are exactly those of the enumeration kernel / the oracle.
 // ---------------------------------------------------------------------------------------------
-constexpr int SX_THREADS = 512;
-struct SxPoint { double x, y; float r; float pad; };  // 24 bytes
+#ifndef SD_SX_THREADS
+#define SD_SX_THREADS 512
+#endif
+constexpr int SX_THREADS = SD_SX_THREADS;
+constexpr int SX_ROWS = 3;
 
-__device__ __forceinline__ int sx_classify(const double e0, const double e1, const double e2, const float ra,
-                                           const float rb, const float rc, const double tol) {
-    // +1 inside for certain, -1 outside for certain, 0 ask the predicate
-    const double pab = (double)ra * (double)rb, pbc = (double)rb * (double)rc, pca = (double)rc * (double)ra;
-    const double kE = 1e-12;
+// +1 inside for certain, -1 outside for certain, 0 ask the predicate.  kE: relative rounding bound of the e's.
+template <typename R>
+__device__ __forceinline__ int sx_classify(const R e0, const R e1, const R e2, const R ra, const R rb, const R rc,
+                                           const R tol, const R kE) {
+    const R pab = ra * rb, pbc = rb * rc, pca = rc * ra;
     const bool pos = e0 > kE * pab && e1 > kE * pbc && e2 > kE * pca;
     const bool neg = e0 < -kE * pab && e1 < -kE * pbc && e2 < -kE * pca;
     if (pos || neg) return 1;
     // orientation of the triangle = sign of e0 + e1 + e2; an edge function of the opposite sign, beyond the band
-    const double D = (e0 + e1) + e2;
-    const double m0 = tol * ((double)ra + (double)rb) * (1.0 + 1e-9) + kE * pab;
-    const double m1 = tol * ((double)rb + (double)rc) * (1.0 + 1e-9) + kE * pbc;
-    const double m2 = tol * ((double)rc + (double)ra) * (1.0 + 1e-9) + kE * pca;
-    const double big = kE * (pab + pbc + pca);
+    const R D = (e0 + e1) + e2, big = (R)3 * kE * (pab + pbc + pca), up = (R)1 + (R)1e-6;
+    const R m0 = tol * (ra + rb) * up + kE * pab, m1 = tol * (rb + rc) * up + kE * pbc, m2 = tol * (rc + ra) * up + kE * pca;
     if (D > big && (e0 < -m0 || e1 < -m1 || e2 < -m2)) return -1;
     if (D < -big && (e0 > m0 || e1 > m1 || e2 > m2)) return -1;
     return 0;
+}
+
+// row t of triple (oa, ob, oc) in float64: certain cases by the edge functions, the rest by the predicate
+__device__ __forceinline__ bool sx_row64(const double *__restrict__ F, const i64 T, const i64 t, const i64 oa,
+                                         const i64 ob, const i64 oc, const double px, const double py,
+                                         const double tol) {
+    const double ax = F[(oa * T + t) * 2], ay = F[(oa * T + t) * 2 + 1];
+    const double bx = F[(ob * T + t) * 2], by = F[(ob * T + t) * 2 + 1];
+    const double cx = F[(oc * T + t) * 2], cy = F[(oc * T + t) * 2 + 1];
+    const double vax = ax - px, vay = ay - py, vbx = bx - px, vby = by - py, vcx = cx - px, vcy = cy - py;
+    const double f0 = vax * vby - vay * vbx, f1 = vbx * vcy - vby * vcx, f2 = vcx * vay - vcy * vax;
+    // |v| <= |vx| + |vy|: an upper bound without square roots
+    const int c2 = sx_classify<double>(f0, f1, f2, fabs(vax) + fabs(vay), fabs(vbx) + fabs(vby), fabs(vcx) + fabs(vcy),
+                                       tol, 1e-12);
+    if (c2) return c2 > 0;
+    const double V[6] = {ax, ay, bx, by, cx, cy}, P2[2] = {px, py};
+    return in_simplex<2>(V, P2, tol);
+}
+
+// Survivors are not followed inline -- one surviving lane would hold its 31 neighbours through rows they have
+// already failed (with a quarter surviving per row, SOME lane of a warp nearly always survives) -- but COMPACTED:
+// a warp appends the triples that passed row 0 to a small queue in shared memory (ballot + prefix), and whenever
+// 32 are waiting it runs them through the other staged rows, one triple per lane; what passes those is queued
+// again and walks the float64 rows 32 at a time.  (inline: 180 ms per query at config-4 size.)
+struct SxQueue {
+    ushort4 *slot;  // [64] (ia, ib, ic, unsure-row bits)
+    int count;      // warp-uniform
+};
+
+__device__ __forceinline__ void sx_push(SxQueue &Q, const bool put, const ushort4 e, const int lane) {
+    const u32 mask = __ballot_sync(0xffffffffu, put);
+    if (put) Q.slot[Q.count + __popc(mask & ((1u << lane) - 1u))] = e;
+    Q.count += __popc(mask);
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(SX_THREADS) simplex2_strict_kernel(const double *__restrict__ F, const i64 N, const i64 T,
                                                                      const i64 *__restrict__ q, const double tol,
                                                                      i64 *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char sx_smem[];
-    SxPoint *pt = reinterpret_cast<SxPoint *>(sx_smem);                 // [m] others at row 0
-    double *pq = reinterpret_cast<double *>(pt + (N - 1));               // [T][2] the query curve
+    const i64 m = N - 1;
+    const int nr = T < SX_ROWS ? (int)T : SX_ROWS;           // staged rows
+    double *pq = reinterpret_cast<double *>(sx_smem);          // [T][2] the query curve
+    float2 *xy = reinterpret_cast<float2 *>(pq + 2 * T);       // [nr][m]
+    float *rr = reinterpret_cast<float *>(xy + (size_t)nr * m);  // [nr][m]
     __shared__ u64 s_red[SX_THREADS / 32];
+    __shared__ ushort4 s_q[SX_THREADS / 32][2][64];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const i64 qi = blockIdx.y;
     const i64 qc = q ? q[qi] : qi;
-    const i64 m = N - 1;
     for (i64 i = threadIdx.x; i < 2 * T; i += blockDim.x) pq[i] = F[qc * T * 2 + i];
     __syncthreads();
-    for (i64 i = threadIdx.x; i < m; i += blockDim.x) {
-        const i64 o = i + (i >= qc);
-        const double vx = F[o * T * 2] - pq[0], vy = F[o * T * 2 + 1] - pq[1];
-        SxPoint p;
-        p.x = vx;
-        p.y = vy;
-        p.r = __double2float_ru(sqrt(vx * vx + vy * vy) * (1.0 + 1e-7));  // upper bound of |v|
-        p.pad = 0.f;
-        pt[i] = p;
+    for (i64 i = threadIdx.x; i < m * nr; i += blockDim.x) {
+        const i64 r = i / m, k = i - r * m;
+        const i64 o = k + (k >= qc);
+        const double vx = F[(o * T + r) * 2] - pq[2 * r], vy = F[(o * T + r) * 2 + 1] - pq[2 * r + 1];
+        xy[i] = make_float2(__double2float_rn(vx), __double2float_rn(vy));
+        rr[i] = __double2float_ru((fabs(vx) + fabs(vy)) * (1.0 + 1e-6));  // upper bound of |v|, rounding included
     }
     __syncthreads();
+    const float tolf = __double2float_ru(tol);
     u64 count = 0;
-    const i64 npairs = m * (m - 1) / 2;
-    for (i64 pid = (i64)blockIdx.x * blockDim.x + threadIdx.x; pid < npairs; pid += (i64)gridDim.x * blockDim.x) {
-        i64 ia, ib;
-        unrank_pair(pid, ia, ib);
-        const SxPoint A = pt[ia], B = pt[ib];
-        const double e0 = A.x * B.y - A.y * B.x;  // orient2(p, a, b)
-        const i64 oa = ia + (ia >= qc), ob = ib + (ib >= qc);
-        for (i64 ic = ib + 1; ic < m; ++ic) {
-            const SxPoint C = pt[ic];
-            const double e1 = B.x * C.y - B.y * C.x;  // orient2(p, b, c)
-            const double e2 = C.x * A.y - C.y * A.x;  // orient2(p, c, a)
-            int cls = sx_classify(e0, e1, e2, A.r, B.r, C.r, tol);
-            if (cls < 0) continue;
-            const i64 oc = ic + (ic >= qc);
-            if (cls == 0) {
-                double V[6];
-                V[0] = F[oa * T * 2]; V[1] = F[oa * T * 2 + 1];
-                V[2] = F[ob * T * 2]; V[3] = F[ob * T * 2 + 1];
-                V[4] = F[oc * T * 2]; V[5] = F[oc * T * 2 + 1];
-                if (!in_simplex<2>(V, pq, tol)) continue;
+    SxQueue Q1 = {s_q[wid][0], 0}, Q2 = {s_q[wid][1], 0};
+
+    // float64 rows of one queued triple per lane
+    auto run64 = [&](const bool have, const ushort4 e) {
+        if (!have) return;
+        const i64 oa = e.x + (e.x >= qc), ob = e.y + (e.y >= qc), oc = e.z + (e.z >= qc);
+        bool all = true;
+        for (int r = 0; r < nr && all; ++r)  // staged rows the float test could not decide
+            if (e.w & (1u << r)) all = sx_row64(F, T, r, oa, ob, oc, pq[2 * r], pq[2 * r + 1], tol);
+        for (i64 t = nr; t < T && all; ++t) all = sx_row64(F, T, t, oa, ob, oc, pq[2 * t], pq[2 * t + 1], tol);
+        count += all;
+    };
+    // staged rows 1 .. nr-1 of one queued triple per lane; survivors go to Q2
+    auto run_rows = [&](const bool have, ushort4 e) {
+        bool alive = have;
+#pragma unroll
+        for (int r = 1; r < SX_ROWS; ++r) {
+            if (r < nr && alive) {
+                const float2 A = xy[(size_t)r * m + e.x], B = xy[(size_t)r * m + e.y], C = xy[(size_t)r * m + e.z];
+                const float e0 = A.x * B.y - A.y * B.x, e1 = B.x * C.y - B.y * C.x, e2 = C.x * A.y - C.y * A.x;
+                const int cls = sx_classify<float>(e0, e1, e2, rr[(size_t)r * m + e.x], rr[(size_t)r * m + e.y],
+                                                   rr[(size_t)r * m + e.z], tolf, 1e-6f);
+                if (cls < 0) alive = false;
+                else if (cls == 0) e.w |= (unsigned short)(1u << r);
             }
-            // remaining rows, early exit
-            bool all = true;
-            for (i64 t = 1; t < T; ++t) {
-                const double px = pq[2 * t], py = pq[2 * t + 1];
-                const double ax = F[(oa * T + t) * 2], ay = F[(oa * T + t) * 2 + 1];
-                const double bx = F[(ob * T + t) * 2], by = F[(ob * T + t) * 2 + 1];
-                const double cx = F[(oc * T + t) * 2], cy = F[(oc * T + t) * 2 + 1];
-                const double vax = ax - px, vay = ay - py, vbx = bx - px, vby = by - py, vcx = cx - px, vcy = cy - py;
-                const double f0 = vax * vby - vay * vbx, f1 = vbx * vcy - vby * vcx, f2 = vcx * vay - vcy * vax;
-                const float ra = __double2float_ru(sqrt(vax * vax + vay * vay) * (1.0 + 1e-7));
-                const float rb = __double2float_ru(sqrt(vbx * vbx + vby * vby) * (1.0 + 1e-7));
-                const float rc = __double2float_ru(sqrt(vcx * vcx + vcy * vcy) * (1.0 + 1e-7));
-                const int c2 = sx_classify(f0, f1, f2, ra, rb, rc, tol);
-                if (c2 > 0) continue;
-                bool in = false;
-                if (c2 == 0) {
-                    const double V[6] = {ax, ay, bx, by, cx, cy}, P2[2] = {px, py};
-                    in = in_simplex<2>(V, P2, tol);
-                }
-                if (!in) { all = false; break; }
-            }
-            count += all;
         }
+        sx_push(Q2, alive, e, lane);
+        if (Q2.count >= 32) {
+            Q2.count -= 32;
+            run64(true, Q2.slot[Q2.count + lane]);
+            __syncwarp();
+        }
+    };
+
+    const i64 npairs = m * (m - 1) / 2;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 base = (i64)blockIdx.x * blockDim.x + wid * 32; base < npairs; base += stride) {  // warp-uniform
+        const i64 pid = base + lane;
+        const bool valid = pid < npairs;
+        i64 ia = 0, ib = 1;
+        if (valid) unrank_pair(pid, ia, ib);
+        const float2 A = xy[ia], B = xy[ib];
+        const float rA = rr[ia], rB = rr[ib];
+        const float e0 = A.x * B.y - A.y * B.x;
+        int nc = valid ? (int)(m - ib - 1) : 0, nmax = nc;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, d));
+        for (int k = 0; k < nmax; ++k) {
+            const i64 ic = ib + 1 + k;
+            bool pass = false;
+            ushort4 e = make_ushort4((unsigned short)ia, (unsigned short)ib, (unsigned short)ic, 0);
+            if (k < nc) {
+                const float2 C = xy[ic];
+                const float e1 = B.x * C.y - B.y * C.x, e2 = C.x * A.y - C.y * A.x;
+                const int cls = sx_classify<float>(e0, e1, e2, rA, rB, rr[ic], tolf, 1e-6f);
+                pass = cls >= 0;
+                e.w = cls == 0 ? 1 : 0;
+            }
+            sx_push(Q1, pass, e, lane);
+            if (Q1.count >= 32) {
+                Q1.count -= 32;
+                run_rows(true, Q1.slot[Q1.count + lane]);
+                __syncwarp();
+            }
+        }
+    }
+    // drain
+    run_rows(lane < Q1.count, Q1.slot[lane < Q1.count ? lane : 0]);
+    Q1.count = 0;
+    __syncwarp();
+    while (Q2.count > 0) {
+        const int take = Q2.count < 32 ? Q2.count : 32;
+        Q2.count -= take;
+        run64(lane < take, Q2.slot[Q2.count + (lane < take ? lane : 0)]);
+        __syncwarp();
     }
     const u64 tot = block_sum_u64(count, s_red);
     if (threadIdx.x == 0 && tot) atomicAdd((u64 *)&out[qi], tot);
@@ -625,14 +695,14 @@ int simplex_depth_device(sd_ctx *ctx, const double *dF, i64 N, i64 T, int d, con
                             (ctx->simplicial_impl == SD_SIMPLICIAL_AUTO && N > SIMPLEX_ENUM_MAX_N)))
         return simplicial2_count_device(ctx, dF, N, 2 * T, T, d_q, nq, tol, d_out);
     cudaStream_t st = ctx->stream;
-    const size_t sx_bytes = (size_t)(N - 1) * sizeof(SxPoint) + (size_t)T * 2 * sizeof(double);
-    if (d == 2 && !relax && N >= 4 && sx_bytes <= 200 * 1024) {
+    const size_t sx_bytes = (size_t)(N - 1) * 12 * (T < SX_ROWS ? T : SX_ROWS) + (size_t)T * 2 * sizeof(double);
+    if (d == 2 && !relax && N >= 4 && sx_bytes <= (size_t)(224 - SX_THREADS / 32) * 1024) {  // static: 1 KB of queues per warp
         // first-row pruning in shared memory; several CTAs per query so that a handful of queries fills the GPU
         SD_CUDA(cudaFuncSetAttribute(simplex2_strict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sx_bytes));
         SD_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nq * sizeof(i64), st));
         const i64 npairs = (N - 1) * (N - 2) / 2;
         i64 slices = ceil_div(npairs, (i64)SX_THREADS * 8);
-        const i64 want = ceil_div(2 * (i64)ctx->sm_count, nq);
+        const i64 want = 2 * (i64)ctx->sm_count / nq;  // one resident CTA per SM: whole waves, no ragged third one
         if (slices > want) slices = want;
         if (slices < 1) slices = 1;
         for (i64 q0 = 0; q0 < nq; q0 += 65535) {
