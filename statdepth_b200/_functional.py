@@ -49,6 +49,8 @@ def _univariate_depths(X: np.ndarray, queries, J: int, relax: bool) -> np.ndarra
                 cnt = _dist.relaxed_counts(lambda Xr, q, jj: eng.band_depth_counts(Xr, q, jj, True), X, queries, j, eng)
             else:
                 qs = np.arange(n, dtype=np.int64) if queries is None else np.asarray(queries, dtype=np.int64)
+                if j == 3:  # strict J = 3 enumerates the C(n-1, 3) triples of every query (bd_triple_kernel)
+                    settings.check_enumeration(float(len(qs)) * binom(n - 1, 3), 'strict band depth with J=3 (n=%d)' % n)
                 cnt = _dist.query_sharded(lambda qb: eng.band_depth_counts(X, qb, j, False), qs, np.int64)
             s_nj = cnt.astype(np.float64)
         elif relax:

@@ -68,7 +68,8 @@ int band_depth_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, const
     {
         const long double full = (j == 2) ? (long double)(n - 1) * (n - 2) / 2.0L
                                           : (long double)(n - 1) * (n - 2) * (n - 3) / 6.0L;
-        if (full * (long double)(T > 0 ? T : 1) >= 9.0e18L) {
+        // j = 3: the kernels form 3 * C(m, 3) before dividing (comb3_dev), so that intermediate must fit as well
+        if (full * (long double)(T > 0 ? T : 1) >= 9.0e18L || (j == 3 && 3.0L * full >= 9.0e18L)) {
             set_error("band depth: T*C(n-1,%d) overflows int64 for T=%lld n=%lld", j, (long long)T, (long long)n);
             return SD_ERR_OVERFLOW;
         }
@@ -168,7 +169,7 @@ static int band_depth_pipelined(sd_ctx *ctx, const double *X, i64 T, i64 n, i64 
     {
         const long double full = (j == 2) ? (long double)(n - 1) * (n - 2) / 2.0L
                                           : (long double)(n - 1) * (n - 2) * (n - 3) / 6.0L;
-        if (full * (long double)T >= 9.0e18L) {
+        if (full * (long double)T >= 9.0e18L || (j == 3 && 3.0L * full >= 9.0e18L)) {
             set_error("band depth: T*C(n-1,%d) overflows int64 for T=%lld n=%lld", j, (long long)T, (long long)n);
             return SD_ERR_OVERFLOW;
         }
