@@ -825,3 +825,51 @@ def test_config4_strict_depth_full_size(engine, oracle):
     assert got.tolist() == exp.tolist() and got[0] > 0
     more = engine.simplex_depth_counts(F, list(range(100, 4900, 300)), False)
     assert more.min() >= 0 and more.max() <= comb(13, 3) + comb(13, 2) * 4986  # at most: triangles with >= 2 anchors
+
+
+def _random_cloud(rng, n):
+    """2-D clouds of trouble: general position, lattices, points on a few lines through a query, clusters within the
+    tolerance band of each other, duplicates, widely different scales."""
+    kind = int(rng.integers(0, 6))
+    P = rng.standard_normal((n, 2))
+    if kind == 1:
+        P = rng.integers(0, int(rng.integers(3, 9)), size=(n, 2)).astype(np.float64)
+    elif kind == 2:  # half of the points on two lines through point 0
+        d = rng.standard_normal((2, 2))
+        k = n // 2
+        P[1:k] = P[0] + rng.uniform(-3, 3, k - 1)[:, None] * d[rng.integers(0, 2, k - 1)]
+    elif kind == 3:  # clusters tighter than the band: members lie within 1e-7 of each other
+        c = rng.standard_normal((max(2, n // 8), 2))
+        P = c[rng.integers(0, len(c), n)] + rng.uniform(-4e-8, 4e-8, (n, 2))
+    elif kind == 4:  # duplicates
+        P[rng.integers(0, n, n // 4)] = P[rng.integers(0, n, n // 4)]
+    elif kind == 5:
+        P = P * rng.choice([1e-3, 1e3]) + rng.choice([0.0, 1e4])
+    return np.ascontiguousarray(P)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_counting_randomized_differential(engine, oracle, seed):
+    """Seeded random clouds / curve sets with degenerate structure: the counting kernels (arcs with a tolerance,
+    exact keys at tolerance 0 on integer data), the strict pruned kernel and the Oja prefix sums against the
+    oracle's enumeration.  Cases within rounding of the band's edge are excluded by construction: structure is exact
+    (lattice, duplicates) or far from the band (1e-7 vs >= 1e-3), except kind 3, which sits INSIDE the band."""
+    from statdepth_b200 import _engine as E
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.choice([65, 80, 130, 200]))
+    P = _random_cloud(rng, n)
+    q = rng.choice(n, size=6, replace=False)
+    tol = float(rng.choice([1e-7, 1e-7, 1e-3]))
+    assert (engine.simplicial_counts(P, q, tol) == oracle.simplicial_counts(P, q, tol)).all()  # AUTO: counted
+    N, T = int(rng.choice([66, 90])), int(rng.integers(2, 6))
+    F = np.stack([_random_cloud(rng, N) for _ in range(T)], axis=1)  # [N, T, 2]: every row a troubled cloud
+    qf = rng.choice(N, size=4, replace=False)
+    assert (engine.simplex_depth_counts(F, qf, True, tol) == oracle.simplex_depth_counts(F, qf, True, tol)).all()
+    assert (engine.simplex_depth_counts(F, qf, False, tol) == oracle.simplex_depth_counts(F, qf, False, tol)).all()
+    try:
+        engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_COUNT)
+        L = rng.integers(0, 7, size=(n, 2)).astype(np.float64)
+        assert (engine.simplicial_counts(L, q, 0.0) == oracle.simplicial_counts(L, q, 0.0)).all()  # exact keys
+        np.testing.assert_allclose(engine.oja(P, 3.0, q), oracle.oja(P, 3.0, q), rtol=1e-10, atol=1e-12)
+    finally:
+        engine.set_option(E.OPT_SIMPLICIAL_IMPL, E.SIMPLICIAL_AUTO)
