@@ -856,6 +856,29 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_subbin_kernel(con
 // persistent: warps claim entries of the work list -- parts of 513..1024 values (sub-bin ranking with 128 bins
 // when `subbin`, the full sorting network otherwise or when a bin overflows) and the parts of at most 512 values
 // whose sub-bin ranking overflowed (sorting network).
+// The overflowed parts of at most 512 values need only the small network (64 registers, 6 KB of shared memory per
+// warp): they get their own persistent kernel at full occupancy instead of waiting in the big-part kernel, whose
+// 128 registers and 12 KB per warp leave 16 warps per SM (one kernel for both: 162 us of a 1.56 ms step).
+template <bool EXTRA>
+__global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_overflow_kernel(const RankArgs a, const RankOut o) {
+    __shared__ u32 s_keys[RANK_WARPS][CAP / 2];
+    __shared__ u32 s_res[RANK_WARPS][CAP / 2];
+    __shared__ u32 s_flag[RANK_WARPS][CAP / 2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int total = a.bigcount[0];
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&a.bigcount[3], 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= total) break;
+        const int2 e = a.biglist[i];
+        const int cnt = a.cursor[(i64)e.x * a.P + e.y];
+        if (cnt > CAP / 2) continue;  // the big-part kernel's
+        if (cnt <= 256) rank_one<8, EXTRA>(a, o, (i64)e.x, e.y, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
+        else rank_one<16, EXTRA>(a, o, (i64)e.x, e.y, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
+    }
+}
+
 template <bool EXTRA>
 __global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const RankArgs a, const RankOut o,
                                                                           const int subbin) {
@@ -873,6 +896,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const 
         const i64 row = e.x;
         const int part = e.y, cnt = a.cursor[row * a.P + part];
         if (cnt <= CAP / 2) {
+            if (subbin) continue;  // overflowed small parts: mbd_rank_overflow_kernel
             rank_one<16, EXTRA>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
             continue;
         }
@@ -1335,20 +1359,29 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             ra.row0 = r0;
             ra.biglist = biglist;
             ra.bigcount = ctx->d_status + 2;
-            SD_CUDA(cudaMemsetAsync(ctx->d_status + 2, 0, 2 * sizeof(int), st));
+            SD_CUDA(cudaMemsetAsync(ctx->d_status + 2, 0, 4 * sizeof(int), st));  // appended | claimed (big) | - | claimed (overflow)
             const dim3 rgrid((unsigned)ceil_div(P, RANK_WARPS), (unsigned)rows);
             const unsigned bgrid = (unsigned)(ctx->sm_count * 4);
+            const unsigned ogrid = (unsigned)(ctx->sm_count * 8);
             if (o.acc3 || o.rank_b || o.group_rows) {
-                if (rank_subbin) mbd_rank_subbin_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
-                else mbd_rank_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                if (rank_subbin) {
+                    mbd_rank_subbin_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                    mbd_rank_overflow_kernel<true><<<ogrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                } else {
+                    mbd_rank_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                }
                 mbd_rank_big_kernel<true><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o, rank_subbin);
             } else {
-                if (rank_subbin) mbd_rank_subbin_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
-                else mbd_rank_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                if (rank_subbin) {
+                    mbd_rank_subbin_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                    mbd_rank_overflow_kernel<false><<<ogrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                } else {
+                    mbd_rank_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                }
                 mbd_rank_big_kernel<false><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o, rank_subbin);
             }
             SD_TRY(prof_end(ctx));
-            ctx->last.launches += 3;
+            ctx->last.launches += rank_subbin ? 4 : 3;
         }
         // rows flagged as overflowing (or all rows when forced): generic path; idle CTAs exit at once
         SD_TRY(prof_begin(ctx, SD_PHASE_MBD_GENERIC));
