@@ -789,7 +789,7 @@ def test_strict_simplex_depth_d2_pruned_kernel(engine, oracle):
     on-edge cases), the reference's collinear fixture, several tolerances and query subsets."""
     from statdepth_b200.testing import generate_noisy_multivariate
     rng = np.random.default_rng(4)
-    for N, T in ((5, 3), (12, 5), (40, 3), (90, 6), (150, 4)):
+    for N, T in ((4, 1), (5, 3), (9, 2), (12, 5), (33, 1), (40, 3), (90, 6), (150, 4)):
         F = rng.standard_normal((N, T, 2)).cumsum(1) * (0.2 if N == 150 else 1.0)
         for tol in (0.0, 1e-7, 0.05):
             assert (engine.simplex_depth_counts(F, None, False, tol) == oracle.simplex_depth_counts(F, None, False, tol)).all()
