@@ -511,6 +511,40 @@ def secondary(c: Ctx):
                   "%d-query sample, host buffers incl. the 20 MB upload)" % nq4,
         "value": nq4 / float(t.item()), "unit": "depth-evals/s", "ms_per_step": float(t.item()) * 1e3, "n_gpus": c.world}
 
+    # ---- cfg4 strict (pruned enumeration, 2.08e10 triples per query) and Oja depth of the 50 000-point cloud ------------
+    nqs = 2 * c.world
+    lo, hi = c.sdist.block(nqs, c.rank, c.world)
+    qs4 = (np.arange(lo, hi, dtype=np.int64) + 1) * (5000 // (nqs + 1))
+    eng.simplex_depth_counts(Fm, qs4[:1], False, 1e-7)
+    if c.world > 1:
+        c.dist.barrier()
+    t0 = time.perf_counter()
+    eng.simplex_depth_counts(Fm, qs4, False, 1e-7)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=c.dev)
+    if c.world > 1:
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    out["cfg4_simplex_depth_strict_d2"] = {
+        "metric": "strict multivariate simplex depth-evals/s (5000 curves x 256 points x 2 channels, relax=False: C(4999,3) = "
+                  "2.08e10 triples per query, rows staged in shared memory; %d-query sample)" % nqs,
+        "value": nqs / float(t.item()), "unit": "depth-evals/s", "ms_per_step": float(t.item()) * 1e3, "n_gpus": c.world}
+    nqo = 2048 * c.world
+    lo, hi = c.sdist.block(nqo, c.rank, c.world)
+    qo = np.arange(lo, hi, dtype=np.int64) * (50_000 // nqo)
+    eng.oja(P, 1.0, qo)
+    if c.world > 1:
+        c.dist.barrier()
+    t0 = time.perf_counter()
+    eng.oja(P, 1.0, qo)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=c.dev)
+    if c.world > 1:
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    out["cfg5_oja_depth"] = {
+        "metric": "Oja depth-evals/s (50 000 points, d = 2: 1.25e9 triangles per query summed by angular prefix sums; "
+                  "%d-query sample, host buffers)" % nqo,
+        "value": nqo / float(t.item()), "unit": "depth-evals/s", "ms_per_step": float(t.item()) * 1e3, "n_gpus": c.world}
+
     # ---- cfg1: call latency of the public API at the reference's own size (rank 0 only, unsharded) -------------
     if c.rank == 0:
         from statdepth_b200 import FunctionalDepth
