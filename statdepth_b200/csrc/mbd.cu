@@ -89,9 +89,11 @@ __device__ __forceinline__ int sp_swz(int g) { return g ^ ((g >> 5) & 31); }
 __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double *__restrict__ X, i64 n, i64 ld,
                                                                    int P, int S, float *__restrict__ splitters_f,
                                                                    unsigned short *__restrict__ tables,
-                                                                   int *__restrict__ status) {
+                                                                   int *__restrict__ rowflag, int *__restrict__ status) {
     __shared__ u32 skey[MAX_SAMPLE];
     __shared__ float s_splf[MAX_PARTS];
+    __shared__ int s_dups;
+    if (threadIdx.x == 0) s_dups = 0;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int W = S >> 10;  // warps that hold samples
     const double *xr = X + (i64)blockIdx.x * ld;
@@ -135,10 +137,20 @@ __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double 
     }
     __syncthreads();
     if (wid < W) {
+        // tie-heavy rows (rounded data: every part holds a handful of values): a quarter of the sorted sample repeating
+        // its neighbour means the sub-bin ranking cannot work (all copies of a value share a bin) -- bit 2 of the row's
+        // flag sends its parts straight to the sorting network
+        int dups = 0;
+#pragma unroll
+        for (int i = 0; i + 1 < 32; ++i) dups += v[i] == v[i + 1];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) dups += __shfl_xor_sync(0xffffffffu, dups, d);
+        if (lane == 0) atomicAdd(&s_dups, dups);
 #pragma unroll
         for (int i = 0; i < 32; ++i) skey[sp_swz(wid * 1024 + lane * 32 + i)] = v[i];
     }
     __syncthreads();
+    if (threadIdx.x == 0 && 4 * s_dups > S) atomicOr(&rowflag[blockIdx.x], 4);
     // splitter p as a float offset from the row reference: what the partition compares, and the reference the part
     // lists store their values against
     float *outf = splitters_f + (i64)blockIdx.x * (P - 1);
@@ -770,7 +782,8 @@ struct RankArgs {
     int P;
     const int *cursor;         // [rows][P] fill counts
     const u32 *pbase;          // [rows][P] exclusive prefix of the fill counts (#values in lower parts)
-    const int *rowflag;        // [rows] bit 0: has parts with > CAP values (all-equal classes), bit 1: generic path
+    const int *rowflag;        // [rows] bit 0: has parts with > CAP values (all-equal classes), bit 1: generic path,
+                               //        bit 2: tie-heavy sample (skip the sub-bin attempt)
     const float *splitters_f;  // [rows][P-1] offsets from the row's reference
     const float *part_x;       // [rows][row_stride] offsets from the part's reference splitter
     const u32 *part_j;         // [rows][row_stride] curve ids
@@ -913,11 +926,12 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_subbin_kernel(con
     const i64 row = blockIdx.y;
     const int part = blockIdx.x * RANK_WARPS + wid;
     if (part >= a.P) return;
-    if (a.rowflag[row] & 2) return;
+    const int flag = a.rowflag[row];
+    if (flag & 2) return;
     const int cnt = a.cursor[row * a.P + part];
     if (cnt == 0 || cnt > CAP) return;
     bool done = false;
-    if (cnt <= CAP / 2) {
+    if (cnt <= CAP / 2 && !(flag & 4)) {  // bit 2: tie-heavy row (mbd_splitters_kernel), not worth the attempt
         const int P = a.P;
         const u32 base = a.pbase[row * P + part];
         const bool have_range = part > 0 && part < P - 1;
@@ -982,7 +996,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const 
             continue;
         }
         bool done = false;
-        if (subbin) {
+        if (subbin && !(a.rowflag[row] & 4)) {
             const int P = a.P;
             const bool have_range = part > 0 && part < P - 1;
             float hi = 0.f;
@@ -1407,7 +1421,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             if (P > 1) {
                 SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SPLITTERS));
                 mbd_splitters_kernel<<<(unsigned)rows, SP_THREADS, 0, st>>>(Xb, n, ld, P, S, splitters_f,
-                                                                            tables, ctx->d_status);
+                                                                            tables, rowflag, ctx->d_status);
                 SD_TRY(prof_end(ctx));
                 ctx->last.launches++;
             }
