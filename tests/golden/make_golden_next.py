@@ -29,7 +29,8 @@ def f(a):
 
 rng = np.random.default_rng(51)
 P = rng.standard_normal((12, 2))
-for containment, K, seed in (("simplex", 2, 7), ("l1", 3, 8), ("simplex", 3, 9)):
+for containment, K, seed in (("simplex", 2, 7), ("l1", 3, 8), ("simplex", 3, 9), ("oja", 2, 3)):  # sampled Oja is 0: its subsets
+    # are drawn from to_compute = [the point] only (_pointcloud.py:182-193)
     np.random.seed(seed)
     res = sd.PointcloudDepth(pd.DataFrame(P), K=K, containment=containment)
     cases.append(dict(kind="pointcloud_K", name="cloud12_%s_K%d_seed%d" % (containment, K, seed), P=f(P), K=K,
