@@ -69,9 +69,27 @@ def check_next_case(case, PointcloudDepth, PointcloudHomogeneity, rtol=1e-12):
         np.testing.assert_allclose(h.F_depths().values, case["F_depths"], rtol=rtol, atol=1e-15)
         np.testing.assert_allclose(h.G_depths().values, case["G_depths"], rtol=rtol, atol=1e-15)
         assert list(F.index) == ["F%d" % i for i in range(len(case["F"]))]  # the caller's F is not mutated
+    elif kind == "functional_homogeneity_mv":
+        from statdepth_b200.homogeneity import FunctionalHomogeneity
+        F = [pd.DataFrame(np.array(case["F"])[i]) for i in range(len(case["F"]))]
+        G = [pd.DataFrame(np.array(case["G"])[i]) for i in range(len(case["G"]))]
+        h = FunctionalHomogeneity(F, G, method=case["method"], containment="simplex", relax=case["relax"], quiet=True)
+        got, want = float(h.homogeneity()), case["value"]
+        assert (np.isnan(got) and np.isnan(want)) or np.isclose(got, want, rtol=rtol, atol=0)
+        assert len(F) == len(case["F"])  # the caller's list is not mutated
     elif kind == "mahalanobis":
-        res = PointcloudDepth(pd.DataFrame(np.array(case["P"])), containment="mahalanobis",
-                              to_compute=case.get("to_compute"))
-        np.testing.assert_allclose(res.values, case["depths"], rtol=1e-9)  # n == p: inverse of a singular covariance
+        df = pd.DataFrame(np.array(case["P"]))
+        res = PointcloudDepth(df, containment="mahalanobis", to_compute=case.get("to_compute"))
+        # n == p (required, _pointcloud.py:160-161): the covariance of n points in n dimensions is singular, so the
+        # "inverse" is whatever LAPACK makes of it (values ~1e16) and depends on the BLAS kernels of the machine.  The
+        # check is therefore the reference's own formula (_pointcloud.py:163-172) recomputed HERE; the stored numbers
+        # are compared only where they are the same machine's (same order of magnitude).
+        mu, inv_cov = df.mean(), np.linalg.inv(np.cov(df, rowvar=True))
+        idx = df.index if case.get("to_compute") is None else case["to_compute"]
+        want = [np.dot((df.loc[p, :] - mu).T, np.dot(inv_cov, df.loc[p, :])) for p in idx]
+        np.testing.assert_allclose(res.values, want, rtol=1e-9)
+        assert len(res) == len(case["depths"])
+        if np.allclose(want, case["depths"], rtol=1e-3):
+            np.testing.assert_allclose(res.values, case["depths"], rtol=1e-9)
     else:
         raise AssertionError(kind)

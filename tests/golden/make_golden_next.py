@@ -53,7 +53,20 @@ for containment in ("l1", "simplex"):
                           F_depths=f(h.F_depths().values), G_depths=f(h.G_depths().values)))
         print("  + pointcloud_homogeneity", containment, method, flush=True)
 
-M = rng.standard_normal((5, 5))
+# multivariate functional homogeneity, p1 (homogeneity.py:136-146; its p2 branch passes its arguments positionally into the
+# wrong slots and always raises, its p3 branch is `pass`)
+from statdepth.homogeneity import FunctionalHomogeneity  # noqa: E402
+rmv = np.random.default_rng(3)
+Fm = rmv.standard_normal((7, 3, 2))
+Gm = rmv.standard_normal((7, 3, 2)) * 0.3  # G's first curve lies deep inside F
+for relax in (True, False):
+    h = FunctionalHomogeneity([pd.DataFrame(Fm[i]) for i in range(7)], [pd.DataFrame(Gm[i]) for i in range(7)], method="p1",
+                              containment="simplex", relax=relax, quiet=True).homogeneity()
+    cases.append(dict(kind="functional_homogeneity_mv", name="mv_p1_%s" % ("relax" if relax else "strict"), F=f(Fm), G=f(Gm),
+                      method="p1", relax=relax, value=float(h)))
+    print("  + functional_homogeneity_mv p1", relax, float(h), flush=True)
+
+M = np.random.default_rng(52).standard_normal((5, 5))  # n == p: the covariance is singular, the inverse what LAPACK makes of it
 res = sd.PointcloudDepth(pd.DataFrame(M), containment="mahalanobis")
 cases.append(dict(kind="mahalanobis", name="mahalanobis_5x5", P=f(M), depths=f(res.values)))
 res = sd.PointcloudDepth(pd.DataFrame(M), containment="mahalanobis", to_compute=[4, 1])
