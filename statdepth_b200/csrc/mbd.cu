@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 4) mbd_rank_big_kernel(const 
         const i64 row = e.x;
         const int part = e.y, cnt = a.cursor[row * a.P + part];
         if (cnt <= CAP / 2) {
-            if (subbin) continue;  // overflowed small parts: mbd_rank_overflow_kernel
+            if (subbin == 2) continue;  // overflowed small parts have their own kernel (mbd_rank_overflow_kernel)
             rank_one<16, EXTRA>(a, o, row, part, cnt, s_keys[wid], s_res[wid], s_flag[wid], lane);
             continue;
         }
@@ -1458,25 +1458,23 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             const dim3 rgrid((unsigned)ceil_div(P, RANK_WARPS), (unsigned)rows);
             const unsigned bgrid = (unsigned)(ctx->sm_count * 4);
             const unsigned ogrid = (unsigned)(ctx->sm_count * 8);
+            // many parts: the overflowed small parts get their own full-occupancy kernel (-15 us at 256 k parts);
+            // few parts (one rank's rows at 8 GPUs): one more persistent launch costs more than it saves (+10 us)
+            const bool split_overflow = rank_subbin && rows * (i64)P >= 100000;
+            const int big_mode = rank_subbin ? (split_overflow ? 2 : 1) : 0;
             if (o.acc3 || o.rank_b || o.group_rows) {
-                if (rank_subbin) {
-                    mbd_rank_subbin_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
-                    mbd_rank_overflow_kernel<true><<<ogrid, RANK_WARPS * 32, 0, st>>>(ra, o);
-                } else {
-                    mbd_rank_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
-                }
-                mbd_rank_big_kernel<true><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o, rank_subbin);
+                if (rank_subbin) mbd_rank_subbin_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                else mbd_rank_kernel<true><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                if (split_overflow) mbd_rank_overflow_kernel<true><<<ogrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                mbd_rank_big_kernel<true><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o, big_mode);
             } else {
-                if (rank_subbin) {
-                    mbd_rank_subbin_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
-                    mbd_rank_overflow_kernel<false><<<ogrid, RANK_WARPS * 32, 0, st>>>(ra, o);
-                } else {
-                    mbd_rank_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
-                }
-                mbd_rank_big_kernel<false><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o, rank_subbin);
+                if (rank_subbin) mbd_rank_subbin_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                else mbd_rank_kernel<false><<<rgrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                if (split_overflow) mbd_rank_overflow_kernel<false><<<ogrid, RANK_WARPS * 32, 0, st>>>(ra, o);
+                mbd_rank_big_kernel<false><<<bgrid, RANK_WARPS * 32, 0, st>>>(ra, o, big_mode);
             }
             SD_TRY(prof_end(ctx));
-            ctx->last.launches += rank_subbin ? 4 : 3;
+            ctx->last.launches += split_overflow ? 4 : 3;
         }
         // rows flagged as overflowing (or all rows when forced): generic path; idle CTAs exit at once
         SD_TRY(prof_begin(ctx, SD_PHASE_MBD_GENERIC));
