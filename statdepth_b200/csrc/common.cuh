@@ -65,6 +65,7 @@ enum BufId {
     BUF_WORK,       // MBD: work list of big parts
     BUF_RANKS,      // strict BD matcher: per-time-point ranks of all curves (packed pairs)
     BUF_GEOM,       // Oja counting: the pool's points and the queries' positions inside the pool
+    BUF_SLAB,       // MBD slab path: per-row maps, bucket tables, bin starts
     NUM_BUFS
 };
 

@@ -1313,12 +1313,69 @@ __global__ void fill_int_kernel(int *p, i64 count, int value) {
     if (i < count) p[i] = value;
 }
 
+}  // namespace sd
+
+#include "mbd_slab.cuh"
+
+namespace sd {
+
 // ---------------------------------------------------------------------------------------------
 // driver
 // ---------------------------------------------------------------------------------------------
 static int pow2ceil_int(i64 v) {
     int p = 1;
     while (p < v) p <<= 1;
+    return p;
+}
+
+// Geometry of the slab path (mbd_slab.cuh) for rows of n values: the fewest CTAs per row whose entries, bin words
+// and bucket table fit one CTA's shared memory.  ok = false: the part pipeline ranks the call.
+struct SlabPlan {
+    bool ok;
+    int G, NBc, NB, ecap, threads;
+    size_t smem_rank, smem_hist;
+};
+
+static int env_int(const char *name, const int fallback) {
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : fallback;
+}
+
+static SlabPlan slab_plan(const double *dX, const i64 n, const i64 ld) {
+    SlabPlan p;
+    memset(&p, 0, sizeof(p));
+    if (const char *e = getenv("SD_MBD_PATH"))
+        if (!strcmp(e, "parts")) return p;  // A/B aid: the part pipeline everywhere
+    i64 min_n = env_int("SD_MBD_SLAB_MIN", (int)SL_MIN_N);
+    if (min_n < SL_MIN_N) min_n = SL_MIN_N;  // the hist kernel samples SL_SAMPLE distinct values
+    // double2 loads need 16-byte aligned rows; 17-bit curve ids
+    if (n < min_n || n > SL_MAX_N || (ld & 1) || ((uintptr_t)dX & 15)) return p;
+    int threads = env_int("SD_MBD_SLAB_THREADS", 1024);
+    if (threads < 128 || threads > 1024 || (threads & 31)) threads = 1024;
+    const int g_forced = env_int("SD_MBD_SLAB_G", 0);
+    const i64 nb0 = ceil_div(n, SL_MEAN);
+    const size_t smem_max = 232448 - 256;  // 227 KB opt-in limit per CTA, less the kernel's static shared memory
+    for (int G = 1; G <= 32; ++G) {
+        if (g_forced > 0 && G != g_forced) continue;
+        // bins per CTA: a multiple of 1024 (every warp sorts the same number of bins), ~SL_MEAN values per bin
+        i64 NBc = ((ceil_div(nb0, G) + 512) / 1024) * 1024;
+        if (NBc < 1024) NBc = 1024;
+        if (n > NBc * G * (SL_MEAN + 1) + NBc * G / 2) NBc += 1024;  // more than 9.5 per bin
+        const i64 per = ceil_div(n, G);
+        const i64 ecap = per + per / 16 + 128;  // bins are allotted by the sample's bucket counts: n/G +- a few percent
+        if (ecap > 65535 || NBc > 65535) continue;
+        const size_t smem = (size_t)(ecap + SL_SORT_CAP) * 4 + (size_t)NBc * 4 + (size_t)NBc * 2;
+        if (smem > smem_max) continue;
+        p.ok = true;
+        p.G = G;
+        p.NBc = (int)NBc;
+        p.NB = (int)(NBc * G);
+        p.ecap = (int)ecap;
+        p.threads = threads;
+        p.smem_rank = smem;
+        p.smem_hist = (size_t)p.NB * 4;
+        break;
+    }
     return p;
 }
 
@@ -1400,6 +1457,37 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
 
     SD_CUDA(cudaFuncSetAttribute(mbd_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
 
+    // slab path (mbd_slab.cuh): per-value codes, bin starts, per-CTA offsets, row flags
+    const SlabPlan sp = ctx->mbd_force_fallback ? SlabPlan{} : slab_plan(dX, n, ld);
+    SlabArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    if (sp.ok) {
+        const size_t rows_cap = (size_t)Tc;
+        const size_t cpitch = (size_t)((n + 3) & ~(i64)3);
+        const size_t off_below = rows_cap * cpitch * sizeof(u32);
+        const size_t off_flag = off_below + rows_cap * sp.G * sizeof(u32);
+        const size_t off_starts = off_flag + rows_cap * sizeof(int);
+        SD_TRY(ctx->buf[BUF_SLAB].reserve(off_starts + rows_cap * sp.NB * sizeof(unsigned short)));
+        unsigned char *base = ctx->buf[BUF_SLAB].as<unsigned char>();
+        sa.n = n;
+        sa.ld = ld;
+        sa.G = sp.G;
+        sa.NBc = sp.NBc;
+        sa.ecap = sp.ecap;
+        sa.codes = reinterpret_cast<u32 *>(base);
+        sa.cpitch = (i64)cpitch;
+        sa.below = reinterpret_cast<u32 *>(base + off_below);
+        sa.rowflag = reinterpret_cast<int *>(base + off_flag);
+        sa.starts = reinterpret_cast<unsigned short *>(base + off_starts);
+        sa.failcount = ctx->d_status + 6;
+        sa.status = ctx->d_status;
+        SD_CUDA(cudaFuncSetAttribute(mbd_slab_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem_hist));
+        SD_CUDA(cudaFuncSetAttribute(mbd_slab_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sp.smem_rank));
+        SD_CUDA(cudaFuncSetAttribute(mbd_slab_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sp.smem_rank));
+    }
+
     RankOut o;
     o.raw2 = d_acc2 ? raw2 : nullptr;
     o.acc3 = want_j3 ? d_acc3 : nullptr;
@@ -1413,7 +1501,37 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     for (i64 r0 = 0; r0 < T; r0 += Tc) {
         const i64 rows = T - r0 < Tc ? T - r0 : Tc;
         const double *Xb = dX + r0 * ld;
-        if (ctx->mbd_force_fallback) {
+        int *flags = rowflag;  // the row flags the generic path reads
+        bool slab_done = false;
+        if (sp.ok) {
+            sa.X = Xb;
+            sa.row0 = r0;
+            SD_CUDA(cudaMemsetAsync(sa.failcount, 0, sizeof(int), st));
+            SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SPLITTERS));
+            mbd_slab_hist_kernel<<<(unsigned)rows, SL_HIST_THREADS, sp.smem_hist, st>>>(sa);
+            SD_TRY(prof_end(ctx));
+            ctx->last.launches++;
+            bool use = true;
+            if (!ctx->async_device) {  // many rows that do not fit (tie-heavy data): the part pipeline ranks the block
+                SD_CUDA(cudaMemcpyAsync(ctx->h_status + 3, sa.failcount, sizeof(int), cudaMemcpyDeviceToHost, st));
+                SD_CUDA(cudaStreamSynchronize(st));
+                use = (i64)ctx->h_status[3] * 16 <= rows;
+            }
+            if (use) {
+                const dim3 sgrid((unsigned)sp.G, (unsigned)rows);
+                SD_TRY(prof_begin(ctx, SD_PHASE_MBD_RANK));
+                if (o.acc3 || o.rank_b || o.group_rows)
+                    mbd_slab_rank_kernel<true><<<sgrid, sp.threads, sp.smem_rank, st>>>(sa, o);
+                else
+                    mbd_slab_rank_kernel<false><<<sgrid, sp.threads, sp.smem_rank, st>>>(sa, o);
+                SD_TRY(prof_end(ctx));
+                ctx->last.launches++;
+                flags = sa.rowflag;
+                slab_done = true;
+            }
+        }
+        if (slab_done) {
+        } else if (ctx->mbd_force_fallback) {
             fill_int_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(rowflag, rows, 2);
             ctx->last.launches++;
         } else {
@@ -1479,7 +1597,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         // rows flagged as overflowing (or all rows when forced): generic path; idle CTAs exit at once
         SD_TRY(prof_begin(ctx, SD_PHASE_MBD_GENERIC));
         const i64 fgrid = rows < 2 * (i64)ctx->sm_count ? rows : 2 * (i64)ctx->sm_count;
-        mbd_fallback_kernel<<<(unsigned)fgrid, 1024, 0, st>>>(Xb, n, ld, NP, rowflag, rows, (u64 *)part_x, NP, r0, o,
+        mbd_fallback_kernel<<<(unsigned)fgrid, 1024, 0, st>>>(Xb, n, ld, NP, flags, rows, (u64 *)part_x, NP, r0, o,
                                                               ctx->d_status, fb_count);
         SD_TRY(prof_end(ctx));
         ctx->last.launches++;
