@@ -98,6 +98,7 @@ struct sd_ctx {
     void *stage[2] = {nullptr, nullptr};                        // pinned staging of pageable host input (api.cu)
     size_t stage_cap[2] = {0, 0};
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_slab = nullptr;                              // MBD slab path: "table kernel's verdict copied" (mbd.cu)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // h2d start | kernels start | kernels end | d2h end
     sd_timings last = {0, 0, 0, 0, 0, 0};
     int bd_impl = SD_BD_AUTO;

@@ -265,6 +265,7 @@ int sd_destroy(sd_ctx *ctx) {
         if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
         if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
     }
+    if (ctx->ev_slab) cudaEventDestroy(ctx->ev_slab);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

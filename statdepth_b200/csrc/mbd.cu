@@ -1364,7 +1364,7 @@ static SlabPlan slab_plan(const double *dX, const i64 n, const i64 ld) {
         const i64 per = ceil_div(n, G);
         const i64 ecap = per + per / 16 + 128;  // bins are allotted by the sample's bucket counts: n/G +- a few percent
         if (ecap > 65535 || NBc > 65535) continue;
-        const size_t smem = (size_t)(ecap + SL_SORT_CAP) * 4 + (size_t)NBc * 4 + (size_t)NBc * 2;
+        const size_t smem = (size_t)(ecap + SL_SORT_CAP) * 4 + (size_t)NBc * 4;
         if (smem > smem_max) continue;
         p.ok = true;
         p.G = G;
@@ -1464,7 +1464,9 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     if (sp.ok) {
         const size_t rows_cap = (size_t)Tc;
         const size_t cpitch = (size_t)((n + 3) & ~(i64)3);
-        const size_t off_below = rows_cap * cpitch * sizeof(u32);
+        const size_t off_map = rows_cap * cpitch * sizeof(u32);
+        const size_t off_tables = off_map + rows_cap * sizeof(double2);
+        const size_t off_below = off_tables + rows_cap * SL_BUCKETS * sizeof(uint2);
         const size_t off_flag = off_below + rows_cap * sp.G * sizeof(u32);
         const size_t off_starts = off_flag + rows_cap * sizeof(int);
         SD_TRY(ctx->buf[BUF_SLAB].reserve(off_starts + rows_cap * sp.NB * sizeof(unsigned short)));
@@ -1476,6 +1478,8 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         sa.ecap = sp.ecap;
         sa.codes = reinterpret_cast<u32 *>(base);
         sa.cpitch = (i64)cpitch;
+        sa.rowmap = reinterpret_cast<double2 *>(base + off_map);
+        sa.tables = reinterpret_cast<uint2 *>(base + off_tables);
         sa.below = reinterpret_cast<u32 *>(base + off_below);
         sa.rowflag = reinterpret_cast<int *>(base + off_flag);
         sa.starts = reinterpret_cast<unsigned short *>(base + off_starts);
@@ -1508,13 +1512,22 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             sa.row0 = r0;
             SD_CUDA(cudaMemsetAsync(sa.failcount, 0, sizeof(int), st));
             SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SPLITTERS));
+            mbd_slab_table_kernel<<<(unsigned)rows, SL_TABLE_THREADS, 0, st>>>(sa);
+            // The table kernel already knows the rows this path cannot take (ties, degenerate ranges).  Its count comes
+            // back while the hist kernel runs, so the host decides without leaving the GPU idle: many unfit rows
+            // (tie-heavy data) send the block to the part pipeline, and the hist kernel has skipped those rows anyway.
+            const bool ask = !ctx->async_device;
+            if (ask) {
+                if (!ctx->ev_slab) SD_CUDA(cudaEventCreateWithFlags(&ctx->ev_slab, cudaEventDisableTiming));
+                SD_CUDA(cudaMemcpyAsync(ctx->h_status + 3, sa.failcount, sizeof(int), cudaMemcpyDeviceToHost, st));
+                SD_CUDA(cudaEventRecord(ctx->ev_slab, st));
+            }
             mbd_slab_hist_kernel<<<(unsigned)rows, SL_HIST_THREADS, sp.smem_hist, st>>>(sa);
             SD_TRY(prof_end(ctx));
-            ctx->last.launches++;
+            ctx->last.launches += 2;
             bool use = true;
-            if (!ctx->async_device) {  // many rows that do not fit (tie-heavy data): the part pipeline ranks the block
-                SD_CUDA(cudaMemcpyAsync(ctx->h_status + 3, sa.failcount, sizeof(int), cudaMemcpyDeviceToHost, st));
-                SD_CUDA(cudaStreamSynchronize(st));
+            if (ask) {
+                SD_CUDA(cudaEventSynchronize(ctx->ev_slab));
                 use = (i64)ctx->h_status[3] * 16 <= rows;
             }
             if (use) {

@@ -34,7 +34,8 @@ constexpr int SL_IDBITS = 17;          // entry = key14 << 17 | curve id  (n <= 
 constexpr int SL_MEAN = 8;             // target values per bin
 constexpr int SL_SORT_CAP = 16;        // bins of at most this many entries are sorted by one thread
 constexpr int SL_BIN_MAX = 255;        // larger bins: the row goes to the generic path
-constexpr int SL_HIST_THREADS = 1024;
+constexpr int SL_TABLE_THREADS = 256;   // table kernel: many small CTAs per SM hide its serial stages
+constexpr int SL_HIST_THREADS = 512;    // pass kernel: two CTAs per SM
 constexpr int SL_SAMPLE = 16384;       // sampled values per row (quads of 4 consecutive values), 16 per thread
 constexpr int SL_SORTED = 1024;        // of which one per thread is sorted for the range
 constexpr int SL_DUPS_MAX = 3;         // equal neighbours tolerated in the sorted sample
@@ -49,6 +50,8 @@ struct SlabArgs {
     const double *X;
     i64 n, ld;
     int G, NBc, ecap;          // CTAs per row, bins per CTA (a multiple of 1024), entries one CTA may hold
+    double2 *rowmap;           // [rows] (s, c): fixed-point position of x = fma(x, s, c)
+    uint2 *tables;             // [rows][SL_BUCKETS] (C, D)
     u32 *codes;                // [rows][cpitch] code(x) of every value: written by hist, streamed by the G rank CTAs
     i64 cpitch;                // n rounded up to a multiple of 4
     unsigned short *starts;    // [rows][G*NBc] first entry position of a bin inside its CTA
@@ -136,57 +139,54 @@ __device__ __forceinline__ u32 slab_block_scan(const u32 v, u32 *wsum, u32 &tota
 }
 
 // ---------------------------------------------------------------------------------------------
-// hist: sample -> range and table; one pass -> exact bin counts -> starts, validation.  One CTA per row.
+// table: sample -> range and code table.  One small CTA per row (the 55 barrier stages of the sample sort and the
+// scattered sample loads are latency, hidden by running many of these CTAs per SM).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SL_HIST_THREADS, 1) mbd_slab_hist_kernel(const SlabArgs a) {
-    extern __shared__ __align__(16) unsigned char sl_smem[];
-    u32 *bins = reinterpret_cast<u32 *>(sl_smem);  // [NB]
+__global__ void __launch_bounds__(SL_TABLE_THREADS) mbd_slab_table_kernel(const SlabArgs a) {
     __shared__ double samp[SL_SORTED];
-    __shared__ uint2 tbl[SL_BUCKETS];
     __shared__ u32 bh[SL_BUCKETS];
     __shared__ u32 wsum[33];
-    __shared__ u32 s_pairwork;
-    const int tid = threadIdx.x, nt = SL_HIST_THREADS;
+    __shared__ int s_dups;
+    const int tid = threadIdx.x, nt = SL_TABLE_THREADS;
     const i64 row = blockIdx.x;
     const int n = (int)a.n;
     const double *xr = a.X + row * a.ld;
-    const double2 *xr2 = reinterpret_cast<const double2 *>(xr);
     const int NB = a.G * a.NBc;
+    // The sample: SL_CHUNKS evenly spaced chunks of 256 consecutive values (coalesced 2 KB reads; scattered 32-byte
+    // quads cost ~160 bytes of DRAM traffic each, 80 % of a full pass for the whole sample).  Thread t reads value t
+    // of every chunk.
+    constexpr int SL_CHUNKS = SL_SAMPLE / SL_TABLE_THREADS;  // 64
+    const i64 gap = ((i64)n - SL_TABLE_THREADS) / (SL_CHUNKS - 1);  // chunk c starts at c * gap: n >= SL_SAMPLE
 
-    // 1. strided sample: 4 quads of 4 consecutive values per thread; one value per thread is sorted for the range
-    double sv[16];
-    {
-        constexpr int NQ = SL_SAMPLE / 4;
-        const i64 nquad = n >> 2;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const i64 quad = ((i64)(tid * 4 + q) * nquad) / NQ;  // distinct quads: n >= SL_SAMPLE
-            const double2 lo2 = xr2[quad * 2], hi2 = xr2[quad * 2 + 1];
-            sv[4 * q] = lo2.x;
-            sv[4 * q + 1] = lo2.y;
-            sv[4 * q + 2] = hi2.x;
-            sv[4 * q + 3] = hi2.y;
-        }
+    // 1. every 16th value of every chunk is sorted for the range
+    for (int i = tid; i < SL_SORTED; i += nt) {
+        const double x = xr[(i64)(i >> 4) * gap + ((i & 15) << 4)];
+        if (slab_nonfinite(x)) atomicOr(a.status, ST_NONFINITE);
+        samp[i] = x;
     }
-    samp[tid] = sv[0];
-    if (tid < SL_BUCKETS) bh[tid] = 0u;
-    if (tid == 0) s_pairwork = 0u;
+    bh[tid] = 0u;
+    if (tid == 0) s_dups = 0;
     for (int k = 2; k <= SL_SORTED; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             __syncthreads();
-            const int p = tid ^ j;
-            if (p > tid) {
-                const double u = samp[tid], v = samp[p];
-                const bool asc = (tid & k) == 0;
+            for (int ce = tid; ce < SL_SORTED / 2; ce += nt) {
+                const int i = ((ce & ~(j - 1)) << 1) | (ce & (j - 1)), p = i | j;
+                const double u = samp[i], v = samp[p];
+                const bool asc = (i & k) == 0;
                 if ((u > v) == asc && u != v) {
-                    samp[tid] = v;
+                    samp[i] = v;
                     samp[p] = u;
                 }
             }
         }
     }
     __syncthreads();
-    const int dups = __syncthreads_count(tid + 1 < SL_SORTED && samp[tid] == samp[tid + 1]);
+    {
+        int d = 0;
+        for (int i = tid; i + 1 < SL_SORTED; i += nt) d += samp[i] == samp[i + 1];
+        if (d) atomicAdd(&s_dups, d);
+    }
+    __syncthreads();
     const double qlo = samp[SL_TRIM], qhi = samp[SL_SORTED - 1 - SL_TRIM];
     const double span = qhi - qlo;
     const double lo = qlo - 0.35 * span, hi = qhi + 0.35 * span;
@@ -194,41 +194,63 @@ __global__ void __launch_bounds__(SL_HIST_THREADS, 1) mbd_slab_hist_kernel(const
     const double c = (4503599627370496.0 + 4294967296.0) - lo * s;
     // rows with ties (continuous data never repeats a value inside a sample of 1024; rounded data does: its equal
     // values would all need the exact path), empty or non-finite ranges: not for this path
-    bool fail = dups > SL_DUPS_MAX || !(span > 0.0) || !(s > 0.0) || slab_nonfinite(s) || slab_nonfinite(c);
-    if (fail) {  // uniform
-        if (tid == 0) {
-            a.rowflag[row] = 2;
-            atomicAdd(a.failcount, 1);
-        }
-        return;
+    const bool fail = s_dups > SL_DUPS_MAX || !(span > 0.0) || !(s > 0.0) || slab_nonfinite(s) || slab_nonfinite(c);
+    if (tid == 0) {
+        a.rowflag[row] = fail ? 2 : 0;
+        if (fail) atomicAdd(a.failcount, 1);
+        else a.rowmap[row] = make_double2(s, c);
     }
+    if (fail) return;  // uniform
 
-    // 2. table from the sample's bucket counts: C[k] = floor(#sample below bucket k * NB * 2^17 / S), D = C[k+1] - C[k]
+    // 2. bucket counts of the whole sample
+    for (int c0 = 0; c0 < SL_CHUNKS; c0 += 8) {
+        double v[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) atomicAdd(&bh[slab_bucket(fma(sv[i], s, c))], 1u);
-    __syncthreads();
-    {
-        const u32 mine = tid < SL_BUCKETS ? bh[tid] : 0u;
-        u32 total;
-        const u32 excl = slab_block_scan(mine, wsum, total);
-        if (tid < SL_BUCKETS) {
-            // codes stay below NB << 17 (values also land in buckets the sample left empty, e.g. beyond its maximum)
-            const u32 top = ((u32)NB << SL_SHIFT) - 1u;
-            const double scl = (double)top / (double)SL_SAMPLE;
-            const u32 c0 = min((u32)((double)excl * scl), top);
-            const u32 c1 = min((u32)((double)(excl + mine) * scl), top);
-            const uint2 e = make_uint2(c0, (tid == 0 || tid == SL_BUCKETS - 1) ? 0u : c1 - c0);
-            tbl[tid] = e;
-        }
+        for (int u = 0; u < 8; ++u) v[u] = xr[(i64)(c0 + u) * gap + tid];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) atomicAdd(&bh[slab_bucket(fma(v[u], s, c))], 1u);
     }
+    __syncthreads();
+    // 3. C[k] = floor(#sample below bucket k * NB * 2^17 / S), D = C[k+1] - C[k]; codes stay below NB << 17 (values
+    //    also land in buckets the sample left empty, e.g. beyond its maximum)
+    const u32 mine = bh[tid];
+    u32 total;
+    const u32 excl = slab_block_scan(mine, wsum, total);
+    const u32 top = ((u32)NB << SL_SHIFT) - 1u;
+    const double scl = (double)top / (double)SL_SAMPLE;
+    const u32 c0 = min((u32)((double)excl * scl), top);
+    const u32 c1 = min((u32)((double)(excl + mine) * scl), top);
+    a.tables[row * SL_BUCKETS + tid] = make_uint2(c0, (tid == 0 || tid == SL_BUCKETS - 1) ? 0u : c1 - c0);
+}
+static_assert(SL_TABLE_THREADS == SL_BUCKETS && SL_SORTED == 16 * (SL_SAMPLE / SL_TABLE_THREADS), "table kernel layout");
+
+// ---------------------------------------------------------------------------------------------
+// hist: ONE pass over the row -> per-value codes, exact bin counts -> starts, validation.  One CTA per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SL_HIST_THREADS, 2) mbd_slab_hist_kernel(const SlabArgs a) {
+    extern __shared__ __align__(16) unsigned char sl_smem[];
+    u32 *bins = reinterpret_cast<u32 *>(sl_smem);  // [NB]
+    __shared__ uint2 tbl[SL_BUCKETS];
+    __shared__ u32 wsum[33];
+    __shared__ u32 s_pairwork;
+    const int tid = threadIdx.x, nt = SL_HIST_THREADS;
+    const i64 row = blockIdx.x;
+    if (a.rowflag[row] & 2) return;  // the table kernel gave the row up
+    const int n = (int)a.n;
+    const double *xr = a.X + row * a.ld;
+    const int NB = a.G * a.NBc;
+    for (int k = tid; k < SL_BUCKETS; k += nt) tbl[k] = a.tables[row * SL_BUCKETS + k];
     for (int b = tid; b < NB; b += nt) bins[b] = 0u;
+    if (tid == 0) s_pairwork = 0u;
+    const double2 sc = a.rowmap[row];
+    const double s = sc.x, c = sc.y;
     __syncthreads();
 
-    // 3. the pass: exact bin counts
+    // 1. the pass
     bool bad = false;
     u32 *crow = a.codes + row * a.cpitch;
     uint2 *crow2 = reinterpret_cast<uint2 *>(crow);
-    slab_stream(xr2, n >> 1, tid, nt, [&](const double2 v, const int p) {
+    slab_stream(reinterpret_cast<const double2 *>(xr), n >> 1, tid, nt, [&](const double2 v, const int p) {
         bad |= slab_nonfinite(v.x) | slab_nonfinite(v.y);
         const u32 c0 = slab_code(v.x, s, c, tbl), c1 = slab_code(v.y, s, c, tbl);
         crow2[p] = make_uint2(c0, c1);
@@ -244,7 +266,7 @@ __global__ void __launch_bounds__(SL_HIST_THREADS, 1) mbd_slab_hist_kernel(const
     if (bad) atomicOr(a.status, ST_NONFINITE);
     __syncthreads();
 
-    // 4. exclusive prefix over the bins (in place), validation, per-CTA starts
+    // 2. exclusive prefix over the bins (in place), validation, per-CTA starts
     const int bpt = (NB + nt - 1) / nt;
     const int b0 = tid * bpt, b1 = min(b0 + bpt, NB);
     u32 sum = 0u, maxc = 0u, pairwork = 0u;
@@ -263,7 +285,7 @@ __global__ void __launch_bounds__(SL_HIST_THREADS, 1) mbd_slab_hist_kernel(const
         run += cnt;
     }
     __syncthreads();
-    fail = maxc > (u32)SL_BIN_MAX || total != (u32)n;
+    bool fail = maxc > (u32)SL_BIN_MAX || total != (u32)n;
     if (tid < a.G) {
         const u32 first = bins[tid * a.NBc];
         const u32 next = tid + 1 < a.G ? bins[(tid + 1) * a.NBc] : (u32)n;
@@ -272,13 +294,25 @@ __global__ void __launch_bounds__(SL_HIST_THREADS, 1) mbd_slab_hist_kernel(const
     }
     if (tid == 0) fail |= s_pairwork > SL_PAIRWORK_MAX;
     fail = __syncthreads_or(fail);
-    if (tid == 0) {
-        a.rowflag[row] = fail ? 2 : 0;
-        if (fail) atomicAdd(a.failcount, 1);
+    if (fail) {
+        if (tid == 0) {
+            a.rowflag[row] = 2;
+            atomicAdd(a.failcount, 1);
+        }
+        return;
     }
-    if (fail) return;
     unsigned short *st = a.starts + row * NB;
-    for (int b = b0; b < b1; ++b) st[b] = (unsigned short)(bins[b] - bins[(b / a.NBc) * a.NBc]);
+    if (b0 < b1) {
+        int edge = (b0 / a.NBc) * a.NBc;  // first bin of the rank CTA that owns bin b
+        u32 first = bins[edge];
+        for (int b = b0; b < b1; ++b) {
+            if (b == edge + a.NBc) {
+                edge = b;
+                first = bins[b];
+            }
+            st[b] = (unsigned short)(bins[b] - first);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -286,9 +320,9 @@ __global__ void __launch_bounds__(SL_HIST_THREADS, 1) mbd_slab_hist_kernel(const
 // ---------------------------------------------------------------------------------------------
 // exact rank of entry m of bin [start, start + cnt): keys first, float64 values where the keys are equal
 template <bool EXTRA>
-__device__ __forceinline__ void slab_rank_entry(const u32 *ents, const int start, const int cnt, const int m,
-                                                const double *__restrict__ xr, const u32 before, const RankOut &o,
-                                                const i64 row_global, const i64 acc_off) {
+__device__ __noinline__ void slab_rank_entry(const u32 *ents, const int start, const int cnt, const int m,
+                                             const double *__restrict__ xr, const u32 before, const RankOut &o,
+                                             const i64 row_global, const i64 acc_off) {
     const u32 mine = ents[start + m];
     const u32 km = mine >> SL_IDBITS;
     u32 less = 0u, eq = 1u;
@@ -307,11 +341,17 @@ __device__ __forceinline__ void slab_rank_entry(const u32 *ents, const int start
 }
 
 // keeps a value (its code, its curve id) if its bin belongs to this CTA: one atomic on the bin's running position
-// places the entry
-__device__ __forceinline__ void slab_keep(const u32 code, const u32 id, u32 *word, u32 *ents, const u32 base_bin,
-                                          const u32 NBc) {
+// places the entry.  word_sa / ents_sa: 32-bit shared-window addresses (the generic-pointer form re-derives the
+// window base for every store: four uniform-datapath instructions per value).
+__device__ __forceinline__ void slab_keep(const u32 code, const u32 id, const u32 word_sa, const u32 ents_sa,
+                                          const u32 base_bin, const u32 NBc) {
     const u32 own = (code >> SL_SHIFT) - base_bin;
-    if (own < NBc) ents[atomicAdd(&word[own], 1u)] = ((code << 14) & 0x7ffe0000u) | id;
+    if (own < NBc) {
+        u32 pos;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(word_sa + 4u * own) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ents_sa + 4u * pos), "r"(((code << 14) & 0x7ffe0000u) | id)
+                     : "memory");
+    }
 }
 
 template <bool EXTRA>
@@ -319,8 +359,6 @@ __global__ void __launch_bounds__(1024, 1) mbd_slab_rank_kernel(const SlabArgs a
     extern __shared__ __align__(16) unsigned char sl_smem[];
     u32 *ents = reinterpret_cast<u32 *>(sl_smem);                        // [ecap + SL_SORT_CAP]
     u32 *word = ents + a.ecap + SL_SORT_CAP;                             // [NBc] running position: start, then end
-    unsigned short *big = reinterpret_cast<unsigned short *>(word + a.NBc);  // [NBc] bins left to step 3
-    __shared__ int s_big;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     const i64 row = blockIdx.y;
     const int g = blockIdx.x;
@@ -332,7 +370,6 @@ __global__ void __launch_bounds__(1024, 1) mbd_slab_rank_kernel(const SlabArgs a
         const unsigned short *st = a.starts + (row * a.G + g) * NBc;
         for (int b = tid; b < NBc; b += nt) word[b] = st[b];
     }
-    if (tid == 0) s_big = 0;
     const u32 bel = a.below[row * a.G + g];
     const u32 base_bin = (u32)g * (u32)NBc;
     __syncthreads();
@@ -340,16 +377,17 @@ __global__ void __launch_bounds__(1024, 1) mbd_slab_rank_kernel(const SlabArgs a
     // 1. stream the row's codes; keep the values of this CTA's bins
     {
         const u32 nbc = (u32)NBc;
+        const u32 ents_sa = (u32)__cvta_generic_to_shared(ents), word_sa = (u32)__cvta_generic_to_shared(word);
         const u32 *crow = a.codes + row * a.cpitch;
         slab_stream(reinterpret_cast<const uint4 *>(crow), n >> 2, tid, nt, [&](const uint4 v, const int p) {
             const u32 id = 4u * (u32)p;
-            slab_keep(v.x, id, word, ents, base_bin, nbc);
-            slab_keep(v.y, id + 1u, word, ents, base_bin, nbc);
-            slab_keep(v.z, id + 2u, word, ents, base_bin, nbc);
-            slab_keep(v.w, id + 3u, word, ents, base_bin, nbc);
+            slab_keep(v.x, id, word_sa, ents_sa, base_bin, nbc);
+            slab_keep(v.y, id + 1u, word_sa, ents_sa, base_bin, nbc);
+            slab_keep(v.z, id + 2u, word_sa, ents_sa, base_bin, nbc);
+            slab_keep(v.w, id + 3u, word_sa, ents_sa, base_bin, nbc);
         });
         const int c = (n & ~3) + tid;
-        if (c < n) slab_keep(crow[c], (u32)c, word, ents, base_bin, nbc);
+        if (c < n) slab_keep(crow[c], (u32)c, word_sa, ents_sa, base_bin, nbc);
     }
     __syncthreads();
 
@@ -357,12 +395,13 @@ __global__ void __launch_bounds__(1024, 1) mbd_slab_rank_kernel(const SlabArgs a
     //    bel + start + i values below it.  word[b] is now the END of bin b (= the start of bin b + 1).  Lane l owns the
     //    stripe [l*Qs, (l+1)*Qs) of the CTA's bins and walks it rotated by l, so that the lanes' words fall into
     //    different banks; every warp does exactly Qs / nw rounds.  The scattered 8-byte REDs of the emission (one L2
-    //    request each) overlap with the next bin's sort.
+    //    request each) overlap with the next bin's sort.  A bin of more than 16 entries, or one with equal keys
+    //    (0.5 % of the bins), is ranked by the whole warp on the exact values right away.
     const i64 row_global = a.row0 + row;
     const i64 acc_off = EXTRA ? acc_offset(o, row_global) : 0;
     const u32 n1 = (u32)n - 1u;
     const int Qs = NBc >> 5;
-    for (int q = wid; q < Qs; q += nw) {
+    for (int q = wid; q < Qs; q += nw) {  // warp-uniform trip count
         int t = q + lane;
         if (t >= Qs) t -= Qs;
         const int b = lane * Qs + t;
@@ -379,25 +418,30 @@ __global__ void __launch_bounds__(1024, 1) mbd_slab_rank_kernel(const SlabArgs a
         u32 gap = 0xffffffffu;
 #pragma unroll
         for (int i = 0; i + 1 < SL_SORT_CAP; ++i) gap = min(gap, e[i + 1] - e[i]);
-        if (cnt <= SL_SORT_CAP && gap >= (1u << SL_IDBITS)) {
+        const bool plain = cnt <= SL_SORT_CAP && gap >= (1u << SL_IDBITS);
+        if (plain) {
             const u32 before = bel + (u32)start;
+            if (EXTRA) {  // rank output / j = 3 / row groups: a rolled loop over the written-back bin (registers)
 #pragma unroll
-            for (int i = 0; i < SL_SORT_CAP; ++i)
-                if (i < cnt) emit_rank<EXTRA>(o, row_global, acc_off, e[i] & SL_IDMASK, before + i, n1 - before - i);
-        } else {  // rare: more than 16 entries, or equal keys -- a warp ranks the bin on the exact values (step 3)
-            big[atomicAdd(&s_big, 1)] = (unsigned short)b;  // at most NBc bins
+                for (int i = 0; i < SL_SORT_CAP; ++i)
+                    if (i < cnt) ents[start + i] = e[i];
+#pragma unroll 1
+                for (int i = 0; i < cnt; ++i)
+                    emit_rank<EXTRA>(o, row_global, acc_off, ents[start + i] & SL_IDMASK, before + i, n1 - before - i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < SL_SORT_CAP; ++i)
+                    if (i < cnt) emit_rank<EXTRA>(o, row_global, acc_off, e[i] & SL_IDMASK, before + i, n1 - before - i);
+            }
         }
-    }
-    __syncthreads();
-
-    // 3. bins of 17..255 entries and bins with equal keys: one warp each, every entry counted against the bin
-    const int nbig = s_big;
-    for (int i = wid; i < nbig; i += nw) {
-        const int b = big[i];
-        const int start = b > 0 ? (int)word[b - 1] : 0;
-        const int cnt = (int)word[b] - start;
-        for (int m = lane; m < cnt; m += 32)
-            slab_rank_entry<EXTRA>(ents, start, cnt, m, xr, bel + (u32)start, o, row_global, acc_off);
+        unsigned todo = __ballot_sync(0xffffffffu, !plain);
+        while (todo) {  // rare
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int bs = __shfl_sync(0xffffffffu, start, src), bc = __shfl_sync(0xffffffffu, cnt, src);
+            for (int m = lane; m < bc; m += 32)
+                slab_rank_entry<EXTRA>(ents, bs, bc, m, xr, bel + (u32)bs, o, row_global, acc_off);
+        }
     }
 }
 
