@@ -89,6 +89,8 @@ enum sd_phase {
     SD_PHASE_MBD_GENERIC = 3,
     SD_PHASE_BD_MASKS = 4,
     SD_PHASE_BD_PAIRS = 5,
+    SD_PHASE_MBD_SLAB_HIST = 6, /* slab path: table + hist kernels (range, code table, per-value codes, bin starts) */
+    SD_PHASE_MBD_SLAB_RANK = 7, /* slab path: rank kernel */
     SD_PHASE_COUNT = 8
 };
 

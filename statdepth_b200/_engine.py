@@ -19,7 +19,8 @@ LAYOUT_TN, LAYOUT_NT = 0, 1
 BD_AUTO, BD_BITS, BD_GEMM, BD_MATCH = 0, 1, 2, 3
 OPT_BD_IMPL, OPT_MBD_FORCE_FALLBACK, OPT_PROFILE, OPT_SIMPLICIAL_IMPL, OPT_ASYNC_DEVICE = 1, 2, 3, 4, 5
 SIMPLICIAL_AUTO, SIMPLICIAL_ENUMERATE, SIMPLICIAL_COUNT = 0, 1, 2
-PHASES = ("mbd_splitters", "mbd_partition", "mbd_rank", "mbd_generic", "bd_masks", "bd_pairs", "p6", "p7")
+PHASES = ("mbd_splitters", "mbd_partition", "mbd_rank", "mbd_generic", "bd_masks", "bd_pairs", "mbd_slab_hist",
+          "mbd_slab_rank")
 
 
 class EngineUnavailable(RuntimeError):

@@ -206,6 +206,7 @@ static int band_depth_pipelined(sd_ctx *ctx, const double *X, i64 T, i64 n, i64 
         }
     }
     // an error inside the loop must not return while a copy out of the caller's buffer is still in flight
+    ctx->mbd_no_wait = 1;  // the host must keep feeding the copy stream while earlier blocks are ranked
     const int loop_status = [&]() -> int {
         int k = 0;
         for (i64 r0 = 0; r0 < T; r0 += RB, ++k) {
@@ -233,6 +234,7 @@ static int band_depth_pipelined(sd_ctx *ctx, const double *X, i64 T, i64 n, i64 
         }
         return SD_OK;
     }();
+    ctx->mbd_no_wait = 0;
     if (loop_status != SD_OK) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamSynchronize(ctx->stream);

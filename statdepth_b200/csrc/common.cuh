@@ -98,11 +98,12 @@ struct sd_ctx {
     void *stage[2] = {nullptr, nullptr};                        // pinned staging of pageable host input (api.cu)
     size_t stage_cap[2] = {0, 0};
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
-    cudaEvent_t ev_slab = nullptr;                              // MBD slab path: "table kernel's verdict copied" (mbd.cu)
+    cudaEvent_t ev_slab[2] = {nullptr, nullptr};                // MBD slab path: unfit-row counts copied (mbd.cu)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // h2d start | kernels start | kernels end | d2h end
     sd_timings last = {0, 0, 0, 0, 0, 0};
     int bd_impl = SD_BD_AUTO;
     int mbd_force_fallback = 0;
+    int mbd_no_wait = 0;    // set around pipelined host calls: mbd_all_device must not wait for device results
     int profile = 0;
     int simplicial_impl = SD_SIMPLICIAL_AUTO;
     int async_device = 0;   // SD_OPT_ASYNC_DEVICE

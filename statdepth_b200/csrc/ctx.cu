@@ -265,7 +265,8 @@ int sd_destroy(sd_ctx *ctx) {
         if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
         if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
     }
-    if (ctx->ev_slab) cudaEventDestroy(ctx->ev_slab);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->ev_slab[i]) cudaEventDestroy(ctx->ev_slab[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -89,7 +89,9 @@ __device__ __forceinline__ int sp_swz(int g) { return g ^ ((g >> 5) & 31); }
 __global__ void __launch_bounds__(SP_THREADS) mbd_splitters_kernel(const double *__restrict__ X, i64 n, i64 ld,
                                                                    int P, int S, float *__restrict__ splitters_f,
                                                                    unsigned short *__restrict__ tables,
-                                                                   int *__restrict__ rowflag, int *__restrict__ status) {
+                                                                   int *__restrict__ rowflag, int *__restrict__ status,
+                                                                   const int *__restrict__ only) {
+    if (only && !(only[blockIdx.x] & 2)) return;  // masked call: only the rows the slab path gave up
     __shared__ u32 skey[MAX_SAMPLE];
     __shared__ float s_splf[MAX_PARTS];
     __shared__ int s_dups;
@@ -267,7 +269,9 @@ __global__ void __launch_bounds__(PT_THREADS, SD_PT_MINB) mbd_partition_kernel(c
                                                                    int *__restrict__ cursor, int *__restrict__ rowflag,
                                                                    float *__restrict__ part_x,
                                                                    u32 *__restrict__ part_j, i64 row_stride,
-                                                                   int *__restrict__ status) {
+                                                                   int *__restrict__ status,
+                                                                   const int *__restrict__ only) {
+    if (only && !(only[blockIdx.y] & 2)) return;
     extern __shared__ __align__(16) unsigned char pt_smem[];
     float *sx = reinterpret_cast<float *>(pt_smem);                   // grouped values (offsets from the part's reference)
     u32 *sj = reinterpret_cast<u32 *>(sx + PT_CHUNK);                 // grouped (part << 12 | index in chunk)
@@ -790,6 +794,7 @@ struct RankArgs {
     const double *X;           // the rows of this block (exact values for run resolution)
     i64 ld;
     i64 row_stride, row0;
+    const int *only;           // masked call: rows are ranked only if only[row] & 2 (null: all rows)
     int2 *biglist;             // (row, part) of parts with more than CAP/2 values
     int *bigcount;             // [0] entries appended, [1] entries claimed
 };
@@ -824,6 +829,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_kernel(const Rank
     const i64 row = blockIdx.y;  // grid: (parts / RANK_WARPS, rows)
     const int part = blockIdx.x * RANK_WARPS + wid;
     if (part >= a.P) return;
+    if (a.only && !(a.only[row] & 2)) return;
     if (a.rowflag[row] & 2) return;  // the whole row goes to the generic path
     const int cnt = a.cursor[row * a.P + part];
     if (cnt == 0 || cnt > CAP) return;  // heavy parts (one value repeated > CAP times): mbd_heavy_kernel
@@ -926,6 +932,7 @@ __global__ void __launch_bounds__(RANK_WARPS * 32, 8) mbd_rank_subbin_kernel(con
     const i64 row = blockIdx.y;
     const int part = blockIdx.x * RANK_WARPS + wid;
     if (part >= a.P) return;
+    if (a.only && !(a.only[row] & 2)) return;
     const int flag = a.rowflag[row];
     if (flag & 2) return;
     const int cnt = a.cursor[row * a.P + part];
@@ -1041,7 +1048,9 @@ __global__ void __launch_bounds__(HV_THREADS) mbd_heavy_kernel(const double *__r
                                                         const int P, const float *__restrict__ splitters_f,
                                                         const unsigned short *__restrict__ tables,
                                                         const int *__restrict__ cursor, int *__restrict__ rowflag,
-                                                        u32 *__restrict__ pbase, const i64 row0, const RankOut o) {
+                                                        u32 *__restrict__ pbase, const i64 row0, const RankOut o,
+                                                        const int *__restrict__ only) {
+    if (only && !(only[blockIdx.x] & 2)) return;
     __shared__ float splf[MAX_PARTS + SPL_PAD];
     __shared__ unsigned short tbl[PT_BUCKETS];
     __shared__ int cnt[MAX_PARTS];
@@ -1505,42 +1514,57 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
     for (i64 r0 = 0; r0 < T; r0 += Tc) {
         const i64 rows = T - r0 < Tc ? T - r0 : Tc;
         const double *Xb = dX + r0 * ld;
-        int *flags = rowflag;  // the row flags the generic path reads
-        bool slab_done = false;
+        const int *only = nullptr;  // part pipeline restricted to the rows the slab path gave up
+        bool slab_done = false, need_generic = true;
         if (sp.ok) {
             sa.X = Xb;
             sa.row0 = r0;
             SD_CUDA(cudaMemsetAsync(sa.failcount, 0, sizeof(int), st));
-            SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SPLITTERS));
+            for (int k = 0; k < 2; ++k)
+                if (!ctx->ev_slab[k]) SD_CUDA(cudaEventCreateWithFlags(&ctx->ev_slab[k], cudaEventDisableTiming));
+            SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SLAB_HIST));
             mbd_slab_table_kernel<<<(unsigned)rows, SL_TABLE_THREADS, 0, st>>>(sa);
-            // The table kernel already knows the rows this path cannot take (ties, degenerate ranges).  Its count comes
-            // back while the hist kernel runs, so the host decides without leaving the GPU idle: many unfit rows
-            // (tie-heavy data) send the block to the part pipeline, and the hist kernel has skipped those rows anyway.
-            const bool ask = !ctx->async_device;
+            // Rows this path cannot take are counted twice: after the table kernel (ties, degenerate ranges) and
+            // after the hist kernel (a bin, a CTA's share or the pair work over its limit: wild tails, adversarial
+            // spreads).  Both counts come back while later kernels run or are already queued, so the host decides
+            // without leaving the GPU idle.  Many unfit rows after the first count (tie-heavy data) send the whole
+            // block to the part pipeline; otherwise the rank kernel skips the flagged rows and the part pipeline
+            // ranks just those.
+            // A pipelined host call (row blocks copied on a second stream while earlier blocks are ranked) and an
+            // SD_OPT_ASYNC_DEVICE call must not stall the host: they skip the counts and always queue the masked part
+            // pipeline behind the rank kernel (its CTAs exit at once when no row is flagged: ~50 us per block).
+            const bool ask = !(ctx->async_device || ctx->mbd_no_wait);
             if (ask) {
-                if (!ctx->ev_slab) SD_CUDA(cudaEventCreateWithFlags(&ctx->ev_slab, cudaEventDisableTiming));
                 SD_CUDA(cudaMemcpyAsync(ctx->h_status + 3, sa.failcount, sizeof(int), cudaMemcpyDeviceToHost, st));
-                SD_CUDA(cudaEventRecord(ctx->ev_slab, st));
+                SD_CUDA(cudaEventRecord(ctx->ev_slab[0], st));
             }
             mbd_slab_hist_kernel<<<(unsigned)rows, SL_HIST_THREADS, sp.smem_hist, st>>>(sa);
             SD_TRY(prof_end(ctx));
             ctx->last.launches += 2;
-            bool use = true;
+            bool all_unfit = false;
             if (ask) {
-                SD_CUDA(cudaEventSynchronize(ctx->ev_slab));
-                use = (i64)ctx->h_status[3] * 16 <= rows;
+                SD_CUDA(cudaMemcpyAsync(ctx->h_status + 2, sa.failcount, sizeof(int), cudaMemcpyDeviceToHost, st));
+                SD_CUDA(cudaEventRecord(ctx->ev_slab[1], st));
+                SD_CUDA(cudaEventSynchronize(ctx->ev_slab[0]));
+                all_unfit = (i64)ctx->h_status[3] * 16 > rows;
             }
-            if (use) {
+            if (!all_unfit) {
                 const dim3 sgrid((unsigned)sp.G, (unsigned)rows);
-                SD_TRY(prof_begin(ctx, SD_PHASE_MBD_RANK));
+                SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SLAB_RANK));
                 if (o.acc3 || o.rank_b || o.group_rows)
                     mbd_slab_rank_kernel<true><<<sgrid, sp.threads, sp.smem_rank, st>>>(sa, o);
                 else
                     mbd_slab_rank_kernel<false><<<sgrid, sp.threads, sp.smem_rank, st>>>(sa, o);
                 SD_TRY(prof_end(ctx));
                 ctx->last.launches++;
-                flags = sa.rowflag;
-                slab_done = true;
+                only = sa.rowflag;  // the flagged rows: part pipeline (the generic path costs ~2 ms per long row)
+                if (ask) {
+                    SD_CUDA(cudaEventSynchronize(ctx->ev_slab[1]));  // the rank kernel is queued behind the hist kernel
+                    if (ctx->h_status[2] == 0) {
+                        slab_done = true;
+                        need_generic = false;
+                    }
+                }
             }
         }
         if (slab_done) {
@@ -1552,7 +1576,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             if (P > 1) {
                 SD_TRY(prof_begin(ctx, SD_PHASE_MBD_SPLITTERS));
                 mbd_splitters_kernel<<<(unsigned)rows, SP_THREADS, 0, st>>>(Xb, n, ld, P, S, splitters_f,
-                                                                            tables, rowflag, ctx->d_status);
+                                                                            tables, rowflag, ctx->d_status, only);
                 SD_TRY(prof_end(ctx));
                 ctx->last.launches++;
             }
@@ -1560,7 +1584,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             SD_TRY(prof_begin(ctx, SD_PHASE_MBD_PARTITION));
             mbd_partition_kernel<<<pgrid, PT_THREADS, PT_SMEM, st>>>(Xb, n, ld, P, splitters_f, tables, cursor,
                                                                      rowflag, part_x, part_j, row_stride,
-                                                                     ctx->d_status);
+                                                                     ctx->d_status, only);
             SD_TRY(prof_end(ctx));
             ctx->last.launches++;
             SD_TRY(prof_begin(ctx, SD_PHASE_MBD_RANK));
@@ -1570,12 +1594,13 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             while (hv_threads < P) hv_threads <<= 1;
             if (n > 16384) hv_threads = HV_THREADS;  // long rows: a heavy row scans n values
             mbd_heavy_kernel<<<(unsigned)rows, hv_threads, 0, st>>>(Xb, n, ld, P, splitters_f, tables, cursor, rowflag, pbase,
-                                                                    r0, o);
+                                                                    r0, o, only);
             RankArgs ra;
             ra.P = P;
             ra.cursor = cursor;
             ra.pbase = pbase;
             ra.rowflag = rowflag;
+            ra.only = only;
             ra.splitters_f = splitters_f;
             ra.X = Xb;
             ra.ld = ld;
@@ -1608,12 +1633,14 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             ctx->last.launches += split_overflow ? 4 : 3;
         }
         // rows flagged as overflowing (or all rows when forced): generic path; idle CTAs exit at once
-        SD_TRY(prof_begin(ctx, SD_PHASE_MBD_GENERIC));
-        const i64 fgrid = rows < 2 * (i64)ctx->sm_count ? rows : 2 * (i64)ctx->sm_count;
-        mbd_fallback_kernel<<<(unsigned)fgrid, 1024, 0, st>>>(Xb, n, ld, NP, flags, rows, (u64 *)part_x, NP, r0, o,
-                                                              ctx->d_status, fb_count);
-        SD_TRY(prof_end(ctx));
-        ctx->last.launches++;
+        if (need_generic) {
+            SD_TRY(prof_begin(ctx, SD_PHASE_MBD_GENERIC));
+            const i64 fgrid = rows < 2 * (i64)ctx->sm_count ? rows : 2 * (i64)ctx->sm_count;
+            mbd_fallback_kernel<<<(unsigned)fgrid, 1024, 0, st>>>(Xb, n, ld, NP, rowflag, rows, (u64 *)part_x, NP, r0, o,
+                                                                  ctx->d_status, fb_count);
+            SD_TRY(prof_end(ctx));
+            ctx->last.launches++;
+        }
         SD_CUDA(cudaGetLastError());
     }
     if (d_acc2) {

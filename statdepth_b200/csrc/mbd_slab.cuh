@@ -31,7 +31,13 @@ namespace sd {
 constexpr int SL_BUCKETS = 256;        // equal-width buckets; 1 .. SL_BUCKETS-2 cover the row's (trimmed, widened) range
 constexpr int SL_SHIFT = 17;           // code = bin << 17 | 17 fractional bits
 constexpr int SL_IDBITS = 17;          // entry = key14 << 17 | curve id  (n <= 131072), bit 31 clear
-constexpr int SL_MEAN = 8;             // target values per bin
+#ifndef SD_SLAB_MEAN
+#define SD_SLAB_MEAN 8
+#endif
+#ifndef SD_SLAB_HIST_MINB
+#define SD_SLAB_HIST_MINB 2            // resident hist CTAs per SM the register budget is held to
+#endif
+constexpr int SL_MEAN = SD_SLAB_MEAN;  // target values per bin
 constexpr int SL_SORT_CAP = 16;        // bins of at most this many entries are sorted by one thread
 constexpr int SL_BIN_MAX = 255;        // larger bins: the row goes to the generic path
 constexpr int SL_TABLE_THREADS = 256;   // table kernel: many small CTAs per SM hide its serial stages
@@ -142,12 +148,12 @@ __device__ __forceinline__ u32 slab_block_scan(const u32 v, u32 *wsum, u32 &tota
 // table: sample -> range and code table.  One small CTA per row (the 55 barrier stages of the sample sort and the
 // scattered sample loads are latency, hidden by running many of these CTAs per SM).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SL_TABLE_THREADS) mbd_slab_table_kernel(const SlabArgs a) {
-    __shared__ double samp[SL_SORTED];
+__global__ void __launch_bounds__(SL_TABLE_THREADS, 4) mbd_slab_table_kernel(const SlabArgs a) {
     __shared__ u32 bh[SL_BUCKETS];
     __shared__ u32 wsum[33];
     __shared__ int s_dups;
-    const int tid = threadIdx.x, nt = SL_TABLE_THREADS;
+    __shared__ float s_q[2];
+    const int tid = threadIdx.x;
     const i64 row = blockIdx.x;
     const int n = (int)a.n;
     const double *xr = a.X + row * a.ld;
@@ -158,42 +164,45 @@ __global__ void __launch_bounds__(SL_TABLE_THREADS) mbd_slab_table_kernel(const 
     constexpr int SL_CHUNKS = SL_SAMPLE / SL_TABLE_THREADS;  // 64
     const i64 gap = ((i64)n - SL_TABLE_THREADS) / (SL_CHUNKS - 1);  // chunk c starts at c * gap: n >= SL_SAMPLE
 
-    // 1. every 16th value of every chunk is sorted for the range
-    for (int i = tid; i < SL_SORTED; i += nt) {
-        const double x = xr[(i64)(i >> 4) * gap + ((i & 15) << 4)];
-        if (slab_nonfinite(x)) atomicOr(a.status, ST_NONFINITE);
-        samp[i] = x;
-    }
-    bh[tid] = 0u;
-    if (tid == 0) s_dups = 0;
-    for (int k = 2; k <= SL_SORTED; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
-            for (int ce = tid; ce < SL_SORTED / 2; ce += nt) {
-                const int i = ((ce & ~(j - 1)) << 1) | (ce & (j - 1)), p = i | j;
-                const double u = samp[i], v = samp[p];
-                const bool asc = (i & k) == 0;
-                if ((u > v) == asc && u != v) {
-                    samp[i] = v;
-                    samp[p] = u;
-                }
-            }
+    // 1. every 16th value of every chunk (1024 values) is sorted for the range: ONE warp, on its registers, as
+    //    order-preserving u32 images of float(x - reference) -- no barrier stages (a 55-stage shared-memory network took
+    //    0.09 ms of a 1.2 ms step); the other warps wait
+    const double x0 = row_reference(xr, n);
+    if (tid < 32) {
+        u32 v[32];
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int e = tid * 32 + i;
+            const double x = xr[(i64)(e >> 4) * gap + ((e & 15) << 4)];
+            bad |= slab_nonfinite(x);
+            v[i] = f32_sortable(__double2float_rn(x - x0));
+        }
+        if (bad) atomicOr(a.status, ST_NONFINITE);
+        warp_bitonic_sort<32, u32>(v, tid);  // element e = lane * 32 + i, ascending
+        int d = 0;
+#pragma unroll
+        for (int i = 0; i + 1 < 32; ++i) d += v[i] == v[i + 1];
+        d += __shfl_down_sync(0xffffffffu, v[0], 1) == v[31] && tid < 31;
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) d += __shfl_xor_sync(0xffffffffu, d, k);
+        const u32 klo = __shfl_sync(0xffffffffu, v[SL_TRIM], 0);
+        const u32 khi = __shfl_sync(0xffffffffu, v[31 - SL_TRIM], 31);
+        if (tid == 0) {
+            s_dups = d;
+            s_q[0] = f32_unsortable(klo);
+            s_q[1] = f32_unsortable(khi);
         }
     }
+    bh[tid] = 0u;
     __syncthreads();
-    {
-        int d = 0;
-        for (int i = tid; i + 1 < SL_SORTED; i += nt) d += samp[i] == samp[i + 1];
-        if (d) atomicAdd(&s_dups, d);
-    }
-    __syncthreads();
-    const double qlo = samp[SL_TRIM], qhi = samp[SL_SORTED - 1 - SL_TRIM];
+    const double qlo = x0 + (double)s_q[0], qhi = x0 + (double)s_q[1];
     const double span = qhi - qlo;
     const double lo = qlo - 0.35 * span, hi = qhi + 0.35 * span;
     const double s = ((double)(SL_BUCKETS - 2) * 4294967296.0) / (hi - lo);
     const double c = (4503599627370496.0 + 4294967296.0) - lo * s;
-    // rows with ties (continuous data never repeats a value inside a sample of 1024; rounded data does: its equal
-    // values would all need the exact path), empty or non-finite ranges: not for this path
+    // rows with ties (continuous data hardly ever repeats a float image inside a sample of 1024; rounded data does:
+    // its equal values would all need the exact path), empty or non-finite ranges: not for this path
     const bool fail = s_dups > SL_DUPS_MAX || !(span > 0.0) || !(s > 0.0) || slab_nonfinite(s) || slab_nonfinite(c);
     if (tid == 0) {
         a.rowflag[row] = fail ? 2 : 0;
@@ -203,12 +212,12 @@ __global__ void __launch_bounds__(SL_TABLE_THREADS) mbd_slab_table_kernel(const 
     if (fail) return;  // uniform
 
     // 2. bucket counts of the whole sample
-    for (int c0 = 0; c0 < SL_CHUNKS; c0 += 8) {
-        double v[8];
+    for (int c0 = 0; c0 < SL_CHUNKS; c0 += 16) {  // loads do not move across atomics: 16 in flight per round
+        double v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = xr[(i64)(c0 + u) * gap + tid];
+        for (int u = 0; u < 16; ++u) v[u] = xr[(i64)(c0 + u) * gap + tid];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) atomicAdd(&bh[slab_bucket(fma(v[u], s, c))], 1u);
+        for (int u = 0; u < 16; ++u) atomicAdd(&bh[slab_bucket(fma(v[u], s, c))], 1u);
     }
     __syncthreads();
     // 3. C[k] = floor(#sample below bucket k * NB * 2^17 / S), D = C[k+1] - C[k]; codes stay below NB << 17 (values
@@ -222,12 +231,13 @@ __global__ void __launch_bounds__(SL_TABLE_THREADS) mbd_slab_table_kernel(const 
     const u32 c1 = min((u32)((double)(excl + mine) * scl), top);
     a.tables[row * SL_BUCKETS + tid] = make_uint2(c0, (tid == 0 || tid == SL_BUCKETS - 1) ? 0u : c1 - c0);
 }
-static_assert(SL_TABLE_THREADS == SL_BUCKETS && SL_SORTED == 16 * (SL_SAMPLE / SL_TABLE_THREADS), "table kernel layout");
+static_assert(SL_TABLE_THREADS == SL_BUCKETS && SL_SORTED == 1024 && SL_SORTED == 16 * (SL_SAMPLE / SL_TABLE_THREADS) && SL_TRIM < 32,
+              "table kernel layout");
 
 // ---------------------------------------------------------------------------------------------
 // hist: ONE pass over the row -> per-value codes, exact bin counts -> starts, validation.  One CTA per row.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SL_HIST_THREADS, 2) mbd_slab_hist_kernel(const SlabArgs a) {
+__global__ void __launch_bounds__(SL_HIST_THREADS, SD_SLAB_HIST_MINB) mbd_slab_hist_kernel(const SlabArgs a) {
     extern __shared__ __align__(16) unsigned char sl_smem[];
     u32 *bins = reinterpret_cast<u32 *>(sl_smem);  // [NB]
     __shared__ uint2 tbl[SL_BUCKETS];

@@ -38,6 +38,12 @@ def rows(kind, T, n):
         return 1e6 + 1e-3 * rng.standard_normal((T, n))
     if kind == "mixed":   # different kinds of rows in one call
         X = rng.standard_normal((T, n)); X[1] = np.round(X[1] * 10); X[2] = 7.0; return X
+    if kind == "tail_all":   # every row fails the hist kernel's validation: masked part pipeline for all rows
+        return rng.standard_cauchy((T, n))
+    if kind == "tail_many":  # 10 of 40 rows: slab ranks 30 rows, the part pipeline the other 10
+        X = rng.standard_normal((T, n)); X[5:15] = rng.standard_cauchy((10, n)); return X
+    if kind == "tail_few":   # 2 of 40 rows: generic path for those
+        X = rng.standard_normal((T, n)); X[7] = rng.standard_cauchy(n); X[30] = rng.standard_cauchy(n); return X
     raise ValueError(kind)
 
 
@@ -45,10 +51,14 @@ bad = cases = 0
 t0 = time.time()
 for n in (16384, 20000, 50000, 100000, 131072):
     for kind in ("normal", "walk", "uniform", "expo", "t3", "cauchy", "round4", "round2", "ints", "const", "outlier",
-                 "shifted", "mixed"):
+                 "shifted", "mixed", "tail_all", "tail_many", "tail_few"):
         T = 4 if n <= 50000 else 3
         if kind == "mixed":  # 2 unfit rows of 40: below the 1/16 threshold, so the slab path keeps the block
             if n > 20000:
+                continue
+            T = 40
+        if kind.startswith("tail_"):
+            if n not in (20000, 100000):
                 continue
             T = 40
         X = rows(kind, T, n)

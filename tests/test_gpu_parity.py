@@ -160,6 +160,84 @@ def test_mbd_full_size_properties(engine, oracle):
     assert (engine.band_depth_counts(Xa, None, 2, True) == oracle.mbd_counts_all(Xa)).all()
 
 
+def _slab_rows(rng, kind, T, n):
+    if kind == "normal":
+        return rng.standard_normal((T, n))
+    if kind == "walk":
+        return rng.standard_normal((T, n)).cumsum(0)
+    if kind == "expo":
+        return rng.standard_exponential((T, n))
+    if kind == "t3":
+        return rng.standard_t(3, (T, n))
+    if kind == "round4":     # moderately tied: the table kernel's sample sees the ties and the part pipeline takes over
+        return np.round(rng.standard_normal((T, n)), 4)
+    if kind == "sparse_ties":  # ties too rare for the sample: the slab path ranks them on the exact values
+        X = rng.standard_normal((T, n))
+        X[:, 1::97] = X[:, 0:-1:97][:, : X[:, 1::97].shape[1]]
+        return X
+    if kind == "shifted":    # spread far below the magnitude
+        return 1e6 + 1e-3 * rng.standard_normal((T, n))
+    if kind == "outliers":   # a few huge values: they clamp into the end buckets and are ranked exactly
+        X = rng.standard_normal((T, n))
+        X[:, ::997] *= 1e9
+        return X
+    if kind == "tail_all":   # heavy tails: every row fails the hist kernel's validation -> masked part pipeline
+        return rng.standard_cauchy((T, n))
+    if kind == "tail_many":  # 10 of 40 rows unfit: the slab path ranks 30 rows, the part pipeline the other 10
+        X = rng.standard_normal((T, n))
+        X[5:15] = rng.standard_cauchy((10, n))
+        return X
+    if kind == "tail_few":   # 2 of 40 rows unfit: generic path for those
+        X = rng.standard_normal((T, n))
+        X[7] = rng.standard_cauchy(n)
+        X[30] = rng.standard_cauchy(n)
+        return X
+    if kind == "mixed":      # a constant row and a rounded row among continuous ones
+        X = rng.standard_normal((T, n))
+        X[1] = np.round(X[1] * 10)
+        X[2] = 7.0
+        return X
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind,n", [("normal", 16384), ("walk", 20000), ("expo", 50000), ("t3", 100000),
+                                    ("normal", 131072), ("round4", 100000), ("sparse_ties", 65536),
+                                    ("shifted", 40000), ("outliers", 100000), ("tail_all", 20000),
+                                    ("tail_many", 100000), ("tail_few", 20000), ("mixed", 30000), ("walk", 16386)])
+def test_mbd_slab_path(engine, oracle, monkeypatch, kind, n):
+    """Rows of 16384 .. 131072 curves take the slab path (csrc/mbd_slab.cuh): counts (j = 2, 3) and ranks equal the
+    oracle's AND the part pipeline's (SD_MBD_PATH=parts) on fit rows, unfit rows and mixtures of both."""
+    rng = np.random.default_rng(4000 + n + len(kind))
+    T = 40 if kind.startswith("tail_") or kind == "mixed" else 5
+    X = _slab_rows(rng, kind, T, n)
+    want2, wb, wa = oracle.mbd_counts_all(X, j=2, want_ranks=True)
+    want3 = oracle.mbd_counts_all(X, j=3)
+    for path in ("slab", "parts"):
+        if path == "parts":
+            monkeypatch.setenv("SD_MBD_PATH", "parts")
+        else:
+            monkeypatch.delenv("SD_MBD_PATH", raising=False)
+        assert (engine.band_depth_counts(X, None, 2, True) == want2).all(), path
+        assert (engine.band_depth_counts(X, None, 3, True) == want3).all(), path
+        below, above = engine.band_ranks(X)
+        assert (below == wb).all() and (above == wa).all(), path
+    q = rng.choice(n, size=7, replace=False)
+    monkeypatch.delenv("SD_MBD_PATH", raising=False)
+    assert (engine.band_depth_counts(X, q, 2, True) == want2[q]).all()
+
+
+def test_mbd_slab_path_is_taken(engine, monkeypatch):
+    """Launch counts tell the paths apart: table + hist + rank + finish on fit data (no generic launch)."""
+    monkeypatch.delenv("SD_MBD_PATH", raising=False)
+    X = walks(5, 8, 50_000)
+    engine.band_depth_counts(X, None, 2, True)
+    tm = engine.timings()
+    assert tm["launches"] <= 5 and tm["fallback_rows"] == 0
+    monkeypatch.setenv("SD_MBD_PATH", "parts")
+    engine.band_depth_counts(X, None, 2, True)
+    assert engine.timings()["launches"] >= 7
+
+
 def _random_matrix(rng, T, n):
     """Random shapes of trouble: continuous, rounded, few classes, constant rows, point masses, tiny spreads."""
     kind = rng.integers(0, 7)
