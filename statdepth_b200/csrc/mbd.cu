@@ -1530,10 +1530,11 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             // without leaving the GPU idle.  Many unfit rows after the first count (tie-heavy data) send the whole
             // block to the part pipeline; otherwise the rank kernel skips the flagged rows and the part pipeline
             // ranks just those.
-            // A pipelined host call (row blocks copied on a second stream while earlier blocks are ranked) and an
-            // SD_OPT_ASYNC_DEVICE call must not stall the host: they skip the counts and always queue the masked part
-            // pipeline behind the rank kernel (its CTAs exit at once when no row is flagged: ~50 us per block).
-            const bool ask = !(ctx->async_device || ctx->mbd_no_wait);
+            // A pipelined host call (row blocks copied on a second stream while earlier blocks are ranked) must not
+            // stall the host: it skips the counts and always queues the masked part pipeline behind the rank kernel
+            // (its CTAs exit at once when no row is flagged: ~50 us per block).  An SD_OPT_ASYNC_DEVICE call does wait:
+            // its waits end with the first two kernels, while the rank kernel is still running.
+            const bool ask = !ctx->mbd_no_wait;
             if (ask) {
                 SD_CUDA(cudaMemcpyAsync(ctx->h_status + 3, sa.failcount, sizeof(int), cudaMemcpyDeviceToHost, st));
                 SD_CUDA(cudaEventRecord(ctx->ev_slab[0], st));
