@@ -311,18 +311,24 @@ __global__ void __launch_bounds__(SL_HIST_THREADS, SD_SLAB_HIST_MINB) mbd_slab_h
         }
         return;
     }
-    unsigned short *st = a.starts + row * NB;
+    // starts relative to the owning rank CTA's first bin, converted in place and copied out coalesced (two per word)
     if (b0 < b1) {
         int edge = (b0 / a.NBc) * a.NBc;  // first bin of the rank CTA that owns bin b
         u32 first = bins[edge];
+        __syncwarp();
         for (int b = b0; b < b1; ++b) {
             if (b == edge + a.NBc) {
                 edge = b;
                 first = bins[b];
             }
-            st[b] = (unsigned short)(bins[b] - first);
+            if (b != edge) bins[b] -= first;  // the edge bins are read by other threads: zeroed after the barrier
         }
     }
+    __syncthreads();
+    if (tid < a.G) bins[tid * a.NBc] = 0u;
+    __syncthreads();
+    u32 *st2 = reinterpret_cast<u32 *>(a.starts + row * NB);  // NB is a multiple of 1024
+    for (int w = tid; w < (NB >> 1); w += nt) st2[w] = bins[2 * w] | (bins[2 * w + 1] << 16);
 }
 
 // ---------------------------------------------------------------------------------------------
