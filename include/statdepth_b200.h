@@ -132,6 +132,12 @@ void *sd_stream(sd_ctx *ctx);
 /* waits for everything queued on sd_stream(); with SD_OPT_ASYNC_DEVICE it completes the pending
  * sd_band_depth_f64_dev call (returns its status, makes sd_get_timings valid) */
 int sd_sync(sd_ctx *ctx);
+/* Which rank pipeline relaxed depth takes for rows of n curves with leading dimension ld, and its geometry (host
+ * arithmetic only: no context, no GPU).  out6[0] = 1: slab path (csrc/mbd_slab.cuh), 0: part pipeline; for the slab
+ * path out6[1] = rank CTAs per row, [2] = bins per CTA, [3] = entries one CTA may hold, [4] / [5] = dynamic shared
+ * memory of the rank / hist kernel in bytes.  The device pointer is assumed 16-byte aligned; the SD_MBD_* environment
+ * variables apply as they do to the depth calls. */
+int sd_mbd_plan(int64_t n, int64_t ld, int64_t *out6);
 
 /*
  * Univariate band depth numerators.  Replaces _univariate_band_depth (_functional.py:198-255)

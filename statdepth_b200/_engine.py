@@ -61,6 +61,7 @@ SIGNATURES = {
     "sd_probe_int8_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "sd_stream": (C.c_void_p, [C.c_void_p]),
     "sd_sync": (C.c_int, [C.c_void_p]),
+    "sd_mbd_plan": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p]),
     "sd_band_depth_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p,
                                     C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "sd_band_depth_f64_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
@@ -108,6 +109,16 @@ def load_library(path: str = None):
 
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def mbd_plan(n: int, ld: int = None) -> dict:
+    """Rank pipeline relaxed depth takes for rows of n curves (host arithmetic of the library, no GPU needed)."""
+    out = np.zeros(6, dtype=np.int64)
+    lib = load_library()
+    if lib.sd_mbd_plan(int(n), int(n if ld is None else ld), _ptr(out)) != 0:
+        raise ValueError(lib.sd_last_error().decode())
+    keys = ("slab", "ctas_per_row", "bins_per_cta", "entries_per_cta", "smem_rank", "smem_hist")
+    return dict(zip(keys, (int(v) for v in out)))
 
 
 class Engine:

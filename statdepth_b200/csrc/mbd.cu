@@ -1655,3 +1655,18 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
 }
 
 }  // namespace sd
+
+extern "C" int sd_mbd_plan(int64_t n, int64_t ld, int64_t *out6) {
+    if (!out6 || n < 1 || ld < n) {
+        sd::set_error("sd_mbd_plan: bad arguments n=%lld ld=%lld", (long long)n, (long long)ld);
+        return SD_ERR_INVALID;
+    }
+    const sd::SlabPlan p = sd::slab_plan(nullptr, n, ld);
+    out6[0] = p.ok ? 1 : 0;
+    out6[1] = p.G;
+    out6[2] = p.NBc;
+    out6[3] = p.ecap;
+    out6[4] = (int64_t)p.smem_rank;
+    out6[5] = (int64_t)p.smem_hist;
+    return SD_OK;
+}

@@ -199,3 +199,32 @@ def test_functional_p3_batched_equals_loop(host_on_oracle, golden):
             Fc.loc[:, col] = G.loc[:, col].values
             loop.append(FunctionalDepth([Fc], to_compute=[col], J=3, relax=relax).loc[col])
         np.testing.assert_allclose(batched, loop, rtol=1e-13)
+
+
+def test_mbd_plan_geometry(monkeypatch):
+    """sd_mbd_plan (host arithmetic of the library, no GPU): the slab path's geometry stays inside what its kernels
+    assume for every eligible row length -- shared memory within the 227 KB opt-in limit, 16-bit bin starts, bins per
+    CTA a multiple of 1024 with 5 .. 9.5 values per bin -- and everything else goes to the part pipeline."""
+    from statdepth_b200._engine import mbd_plan
+    for k in ("SD_MBD_PATH", "SD_MBD_SLAB_MIN", "SD_MBD_SLAB_G", "SD_MBD_SLAB_THREADS"):
+        monkeypatch.delenv(k, raising=False)
+    for n in (1, 200, 16382, 131074, 250_000):
+        assert mbd_plan(n)["slab"] == 0
+    assert mbd_plan(20_001, 20_001)["slab"] == 0 and mbd_plan(20_000, 20_001)["slab"] == 0  # odd leading dimension
+    rng = __import__("numpy").random.default_rng(0)
+    sizes = [16384, 16386, 20_000, 50_000, 65_536, 100_000, 131_070, 131_072] + \
+        [int(2 * v) for v in rng.integers(8192, 65536, size=200)]
+    for n in sizes:
+        p = mbd_plan(n)
+        assert p["slab"] == 1, n
+        G, nbc, ecap = p["ctas_per_row"], p["bins_per_cta"], p["entries_per_cta"]
+        assert 1 <= G <= 8 and nbc % 1024 == 0 and nbc >= 1024
+        assert p["smem_rank"] == 4 * (ecap + 16) + 4 * nbc and p["smem_rank"] <= 232448 - 256
+        assert p["smem_hist"] == 4 * G * nbc and p["smem_hist"] + 2192 <= 232448 // 2
+        assert ecap <= 65535 and ecap * G >= n * 1.05        # a CTA's share of the row with slack, 16-bit starts
+        assert G * nbc * (1 << 17) < 2 ** 32                   # codes: bin << 17 | fraction in 32 bits
+        assert 4.0 <= n / (G * nbc) <= 9.5, (n, G, nbc)
+    assert mbd_plan(100_000) == {"slab": 1, "ctas_per_row": 3, "bins_per_cta": 4096, "entries_per_cta": 35545,
+                                 "smem_rank": 4 * (35545 + 16) + 4 * 4096, "smem_hist": 4 * 3 * 4096}
+    monkeypatch.setenv("SD_MBD_PATH", "parts")
+    assert mbd_plan(100_000)["slab"] == 0
