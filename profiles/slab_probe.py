@@ -7,7 +7,7 @@ sys.path.insert(0, '.')
 import torch
 from statdepth_b200 import _engine as E
 
-n, T = 100_000, 1024
+n, T = 100_000, int(os.environ.get("PROBE_T", "1024"))
 steps = int(os.environ.get("PROBE_STEPS", "10"))
 eng = E.get_engine(0)
 eng.set_option(E.OPT_PROFILE, 1)
@@ -17,14 +17,14 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 g = torch.Generator(device=dev); g.manual_seed(1)
 X = torch.empty((T, n), dtype=torch.float64, device=dev)
 for r0 in range(0, T, 128):
-    X[r0:r0 + 128] = torch.randn((128, n), dtype=torch.float64, device=dev, generator=g)
+    X[r0:r0 + 128] = torch.randn((min(128, T - r0), n), dtype=torch.float64, device=dev, generator=g)
 X = X.cumsum(0)
 if os.environ.get("PROBE_TIES"):
     X = X.round()
 out = torch.zeros(n, dtype=torch.int64, device=dev)
 configs = sys.argv[1:] or ["parts:SD_MBD_PATH=parts", "slab:"]
 ref = None
-KEYS = ("SD_MBD_PATH", "SD_MBD_SLAB_G", "SD_MBD_SLAB_THREADS", "SD_MBD_SLAB_MIN")
+KEYS = ("SD_MBD_PATH", "SD_MBD_SLAB_G", "SD_MBD_SLAB_THREADS", "SD_MBD_SLAB_MIN", "SD_MBD_SLAB_HIST_THREADS")
 for cfg in configs:
     name, _, envs = cfg.partition(":")
     for k in KEYS:

@@ -1494,7 +1494,10 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
         sa.starts = reinterpret_cast<unsigned short *>(base + off_starts);
         sa.failcount = ctx->d_status + 6;
         sa.status = ctx->d_status;
-        SD_CUDA(cudaFuncSetAttribute(mbd_slab_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem_hist));
+        SD_CUDA(cudaFuncSetAttribute(mbd_slab_hist_kernel<SL_HIST_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sp.smem_hist));
+        SD_CUDA(cudaFuncSetAttribute(mbd_slab_hist_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sp.smem_hist));
         SD_CUDA(cudaFuncSetAttribute(mbd_slab_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sp.smem_rank));
         SD_CUDA(cudaFuncSetAttribute(mbd_slab_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1539,7 +1542,10 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
                 SD_CUDA(cudaMemcpyAsync(ctx->h_status + 3, sa.failcount, sizeof(int), cudaMemcpyDeviceToHost, st));
                 SD_CUDA(cudaEventRecord(ctx->ev_slab[0], st));
             }
-            mbd_slab_hist_kernel<<<(unsigned)rows, SL_HIST_THREADS, sp.smem_hist, st>>>(sa);
+            if (env_int("SD_MBD_SLAB_HIST_THREADS", rows <= (i64)ctx->sm_count ? 1024 : SL_HIST_THREADS) == 1024)
+                mbd_slab_hist_kernel<1024><<<(unsigned)rows, 1024, sp.smem_hist, st>>>(sa);
+            else
+                mbd_slab_hist_kernel<SL_HIST_THREADS><<<(unsigned)rows, SL_HIST_THREADS, sp.smem_hist, st>>>(sa);
             SD_TRY(prof_end(ctx));
             ctx->last.launches += 2;
             bool all_unfit = false;

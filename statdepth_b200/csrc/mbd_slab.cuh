@@ -237,13 +237,16 @@ static_assert(SL_TABLE_THREADS == SL_BUCKETS && SL_SORTED == 1024 && SL_SORTED =
 // ---------------------------------------------------------------------------------------------
 // hist: ONE pass over the row -> per-value codes, exact bin counts -> starts, validation.  One CTA per row.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SL_HIST_THREADS, SD_SLAB_HIST_MINB) mbd_slab_hist_kernel(const SlabArgs a) {
+// NT = 512 (two CTAs per SM) when there are rows enough to fill the machine twice over, 1024 (one per SM) for the short
+// blocks of a multi-GPU rank or a pipelined host call: a CTA's warps are what hides its DRAM latency.
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == SL_HIST_THREADS ? SD_SLAB_HIST_MINB : 1) mbd_slab_hist_kernel(const SlabArgs a) {
     extern __shared__ __align__(16) unsigned char sl_smem[];
     u32 *bins = reinterpret_cast<u32 *>(sl_smem);  // [NB]
     __shared__ uint2 tbl[SL_BUCKETS];
     __shared__ u32 wsum[33];
     __shared__ u32 s_pairwork;
-    const int tid = threadIdx.x, nt = SL_HIST_THREADS;
+    const int tid = threadIdx.x, nt = NT;
     const i64 row = blockIdx.x;
     if (a.rowflag[row] & 2) return;  // the table kernel gave the row up
     const int n = (int)a.n;
