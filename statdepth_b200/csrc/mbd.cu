@@ -6,7 +6,12 @@
 //     #{j-subsets whose closed band contains c} = C(n-1,j) - C(b,j) - C(a,j)
 // so the whole relaxed numerator is a per-row ranking problem (kernel "K1").
 //
-// Pipeline per block of time rows (all kernels on ctx->stream, no host sync):
+// Two pipelines produce the same integers.  Rows of 16 384 .. 131 072 curves take the SLAB path of mbd_slab.cuh
+// (included below: the row stays on the chip, three CTAs per row sort whole bins per thread); this file holds the
+// PART pipeline, which ranks every other row length, the rows the slab path declines (ties, wild tails; under a row
+// mask) and everything under SD_MBD_PATH=parts, and the driver that chooses (mbd_all_device).
+//
+// Part pipeline per block of time rows (all kernels on ctx->stream, no host sync):
 //   1. mbd_splitters_kernel : one CTA per row sorts a strided sample (u32 images of float(x - ref), register
 //                             bitonic network per warp + swizzled shared-memory merges) and emits P-1
 //                             equal-mass splitters.
@@ -1575,6 +1580,7 @@ int mbd_all_device(sd_ctx *ctx, const double *dX, i64 T, i64 n, i64 ld, bool wan
             }
         }
         if (slab_done) {
+            // every row of the block has been ranked by the slab path
         } else if (ctx->mbd_force_fallback) {
             fill_int_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(rowflag, rows, 2);
             ctx->last.launches++;
