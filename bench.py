@@ -562,6 +562,22 @@ def secondary(c: Ctx):
                                           "higher_is_better": False, "n_gpus": 1}
     if c.world > 1:
         c.dist.barrier()
+
+    # ---- cfg2 once more through the part pipeline (SD_MBD_PATH=parts): the A/B of the headline's slab path, same box,
+    #      same process, same sharding.  Every rank runs it (the step holds a collective); a failure only drops the entry.
+    try:
+        os.environ["SD_MBD_PATH"] = "parts"
+        r = bench_band(c, 100_000, 1024, True, "auto", 100_000, steps=10, warmup=3, seed=1, want_e2e=False)
+        ms = r["ms"] / 10
+        out["cfg2_part_pipeline"] = {
+            "metric": METRIC + " (cfg2 ranked by the part pipeline, SD_MBD_PATH=parts: what the headline's slab path replaces)",
+            "value": 100_000 / (ms / 1e3), "unit": "depth-evals/s", "ms_per_step": ms, "n_gpus": c.world,
+            "kernel_ms_per_step": r["kern_ns"] / 1e6 / 10,
+            "phase_ms_per_step": {k: v / 1e6 / 10 for k, v in r["phases"].items()}}
+    except Exception as exc:  # noqa: BLE001
+        out["cfg2_part_pipeline"] = {"error": repr(exc)}
+    finally:
+        os.environ.pop("SD_MBD_PATH", None)
     return out
 
 
