@@ -205,7 +205,9 @@ def test_mbd_plan_geometry(monkeypatch):
     """sd_mbd_plan (host arithmetic of the library, no GPU): the slab path's geometry stays inside what its kernels
     assume for every eligible row length -- shared memory within the 227 KB opt-in limit, 16-bit bin starts, bins per
     CTA a multiple of 1024 with 5 .. 9.5 values per bin -- and everything else goes to the part pipeline."""
+    from statdepth_b200 import build
     from statdepth_b200._engine import mbd_plan
+    build.build()  # no-op when libsdepth.so is up to date
     for k in ("SD_MBD_PATH", "SD_MBD_SLAB_MIN", "SD_MBD_SLAB_G", "SD_MBD_SLAB_THREADS"):
         monkeypatch.delenv(k, raising=False)
     for n in (1, 200, 16382, 131074, 250_000):

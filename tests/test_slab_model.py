@@ -13,7 +13,9 @@ SL_BUCKETS, SL_SHIFT, SL_SAMPLE, SL_TRIM, CHUNK = 256, 17, 16384, 4, 256
 
 
 def plan(n):
+    from statdepth_b200 import build
     from statdepth_b200._engine import mbd_plan
+    build.build()  # no-op when libsdepth.so is up to date
     p = mbd_plan(n)
     assert p["slab"] == 1
     return p["ctas_per_row"], p["bins_per_cta"], p["entries_per_cta"]
