@@ -115,7 +115,7 @@ struct sd_ctx {
     int64_t phase_ns[SD_PHASE_COUNT] = {};
     sd::DevBuf buf[sd::NUM_BUFS];
     int *d_status = nullptr;  // device int[4]: [0] status bits, [1] MBD rows ranked by the generic path
-    int *h_status = nullptr;  // pinned mirror
+    int *h_status = nullptr;  // pinned mirror; [2] and [3] also receive the slab path's unfit-row counts mid-call (mbd.cu)
 };
 
 namespace sd {
